@@ -1,0 +1,162 @@
+/* valor_b200 — C ABI of the B200-native kernels behind VALOR's tri-modal pretraining step.
+ *
+ * The reference (TXH-mercury/VALOR) has no FFI / operator registry: its only seams are the
+ * Python module classes and functions named below.  Each entry point here
+ * states the reference interface whose arithmetic it replaces (file:line under the
+ * reference root).  INTEGRATION.md shows the Python-side binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; the caller owns all memory
+ *     (outputs, workspaces, saved-for-backward tensors); nothing is retained past return;
+ *   - `dtype`: 0 = fp32 (parity mode), 1 = bf16 (perf mode).  Parameters that are vectors
+ *     (bias, LayerNorm gamma/beta, embedding tables, bias tables) are always fp32; gradients
+ *     of parameters are always accumulated (+=) into fp32 buffers;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync,
+ *     no allocation: every entry point is CUDA-graph capturable and re-entrant;
+ *   - return 0 on success, non-zero on error with a message in valor_last_error().
+ */
+#ifndef VALOR_B200_H
+#define VALOR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VALOR_DT_F32 0
+#define VALOR_DT_BF16 1
+
+#define VALOR_ACT_NONE 0
+#define VALOR_ACT_GELU 1      /* erf GELU: model/bert.py:52-57, model/transformer.py:32-38, nn.GELU (videoswin.py:58) */
+#define VALOR_ACT_QUICKGELU 2 /* model/clip.py:167-169 */
+#define VALOR_ACT_RELU 3      /* model/pretrain.py:105 */
+
+#define VALOR_BACKEND_AUTO 0
+#define VALOR_BACKEND_TENSOR 1 /* tcgen05 / TMEM / TMA (bf16 only) */
+#define VALOR_BACKEND_SIMT 2
+
+const char* valor_last_error(void);
+int valor_version(void);
+int valor_num_sms(void);
+
+/* ---- GEMM + fused epilogue -----------------------------------------------------------------
+ * Replaces every nn.Linear / torch.matmul(addmm) on the path: Swin qkv/proj/fc1/fc2/reduction
+ * (videoswin.py:62-64,129-131,251), AST linears (transformer.py:109,136-137), BERT
+ * query/key/value/dense (bert.py:233-235,303-305,347,360,399,412), heads (modeling.py:237,240;
+ * pretrain.py:36,104-112) and their autograd gradients (dgrad / wgrad forms).
+ *   C[M,N] (+)= epi( alpha * A[M,K] . B[N,K]^T )
+ *   a_kmajor=1: A stored [M,K] row-major (pitch lda);  0: stored [K,M] row-major (pitch lda)
+ *   b_kmajor=1: B stored [N,K] row-major (pitch ldb);  0: stored [K,N] row-major (pitch ldb)
+ *   epi(x) = act(x + bias) [* act'(act_aux) instead of act when act_aux != NULL] + residual
+ */
+typedef struct ValorGemmEpilogue {
+  const float* bias;    /* [N] or NULL */
+  const void* residual; /* [M,N] pitch ldr, dtype res_dtype, or NULL */
+  const void* act_aux;  /* [M,N] pitch ld_aux: pre-activation saved by the forward, or NULL */
+  void* preact_out;     /* [M,N] pitch ld_pre: receives x + bias (before act), or NULL */
+  long long ldr, ld_aux, ld_pre;
+  int res_dtype, aux_dtype;
+  int act;
+  int out_dtype;
+  int accumulate; /* C += (fp32 C only); required for split-K */
+  float alpha;
+} ValorGemmEpilogue;
+
+int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor,
+               void* C, long long ldc, int M, int N, int K, const ValorGemmEpilogue* ep, int backend, int force_bn,
+               int force_splits, void* stream);
+
+/* ---- LayerNorm: apex FusedLayerNorm (apex/apex/normalization/fused_layer_norm.py:129-161,
+ * apex/csrc/layer_norm_cuda_kernel.cu) and nn.LayerNorm (videoswin.py:181,187,252,439) ------- */
+int valor_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                        float* rstd, long long M, int N, float eps, void* stream);
+int valor_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma, const float* mean,
+                        const float* rstd, void* dx, float* dgamma, float* dbeta, long long M, int N, void* stream);
+
+/* ---- F.normalize(dim=-1) on contrastive features (pretrain.py:276,283,289) -------------------- */
+int valor_l2norm_fwd(int dtype, const void* x, void* y, float* nrm, long long M, int N, void* stream);
+int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm, void* dx, long long M, int N,
+                     void* stream);
+
+/* ---- multi-head attention: BertSelfAttention / BertCrossAttention (bert.py:244-340) and AST
+ * MultiHeadAttention (transformer.py:115-130).  P problems (sequences) x H heads; problem p has
+ * Nq query rows starting at q_row0[p] (NULL: p*Nq) of Q and kv_len[p] (NULL: max_nk) key rows
+ * starting at kv_row0[p] (NULL: p*max_nk) of K/V; head h occupies columns [h*hd,(h+1)*hd).
+ * scores = q.k^T * scale + mask, mask = -10000 where key_valid[p,j]==0 or (causal[p] && j>i)
+ * (bert.py:869-885).  lse [P,H,Nq] fp32 is saved for the backward.
+ * Backward: dQ written; dK/dV accumulated with += into fp32 [rows, H*hd] buffers the caller
+ * zero-fills (K/V rows shared by several problems add up). */
+int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
+                  void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
+                  const int* kv_row0, const int* kv_len, const unsigned char* key_valid, const unsigned char* causal,
+                  float scale, int backend, void* stream);
+int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                  long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ,
+                  long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd, int Nq,
+                  int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
+                  const unsigned char* key_valid, const unsigned char* causal, float scale, int backend, void* stream);
+
+/* ---- VideoSwin shifted-window attention: WindowAttention3D.forward (videoswin.py:137-163)
+ * together with torch.roll / window_partition / window_reverse / compute_mask
+ * (videoswin.py:75-84,191-226,272-285), evaluated in place on the natural [B,D,H,W] token
+ * order.  qkv [B*D*H*W, 3*heads*hd] (q | k | v), O [B*D*H*W, heads*hd].  (wd,wh,ww)/(sd,sh,sw)
+ * are the EFFECTIVE window / shift (get_window_size, videoswin.py:86-99); (WD,WH,WW) the
+ * configured window that sizes `table` = relative_position_bias_table [(2WD-1)(2WH-1)(2WW-1), heads].
+ * Backward: dqkv's q third is written, k/v thirds accumulate into fp32 dK/dV [tokens, heads*hd]
+ * (caller zero-fills); dtable accumulates (+=). */
+int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, long long ldo, float* lse,
+                          const float* table, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh,
+                          int sw, int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream);
+int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
+                          const float* lse, const float* table, void* dQ, long long lddq, float* dK, float* dV,
+                          long long lddkv, float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd,
+                          int sh, int sw, int WD, int WH, int WW, int heads, int hd, float scale, int backend,
+                          void* stream);
+
+/* ---- data movement around the GEMMs --------------------------------------------------------- */
+/* PatchEmbed3D as GEMM (videoswin.py:361-369): video [B,F,3,Hh,Ww] -> cols [B*F*Hh/4*Ww/4, 96] */
+int valor_swin_im2col(int in_dtype, int dtype, const void* video, void* cols, int B, int F, int Hh, int Ww, void* stream);
+/* AudioEmbeddings conv as GEMM (modeling.py:752-754): spec [BA,mel,frames] -> cols [BA*P, ps*ps] */
+int valor_audio_im2col(int in_dtype, int dtype, const void* spec, void* cols, int BA, int mel, int frames, int ps, void* stream);
+/* cls + position embeddings (modeling.py:755-760) */
+int valor_ast_assemble_fwd(int dtype, const void* tok, const float* cls, const float* pos, void* x, int BA, int P, int Hd, void* stream);
+int valor_ast_assemble_bwd(int dtype, const void* dx, void* dtok, float* dcls, float* dpos, int BA, int P, int Hd, void* stream);
+/* BertEmbeddings lookup (bert.py:203-215) */
+int valor_bert_embed_fwd(int dtype, const long long* tokens, const float* word, const float* pos, const float* type0, void* e, long long R, int Tn, int Hd, void* stream);
+int valor_bert_embed_bwd(int dtype, const void* de, const long long* tokens, float* dword, float* dpos, float* dtype0, long long R, int Tn, int Hd, void* stream);
+/* get_multimodal_forward_input_{video,audio} (modeling.py:485-502) into the cross-attention source */
+int valor_media_input_fwd(int dtype, const void* in, const float* frame_emb, const float* type_emb, void* out, int B, int nf, int X, int Hd, int S_total, int row0, void* stream);
+int valor_media_input_bwd(int dtype, const void* dout, void* din, float* dframe, float* dtype_emb, int B, int nf, int X, int Hd, int S_total, int row0, void* stream);
+/* PatchMerging 2x2 gather (videoswin.py:261-265); inverse=1 is its gradient */
+int valor_patch_merge(int dtype, const void* src, void* dst, long long BD, int H, int W, int C, int inverse, void* stream);
+/* mean over the 49 spatial tokens per frame (modeling.py:389) */
+int valor_mean_pool_fwd(int dtype, const void* x, void* y, long long R, int X, int C, void* stream);
+int valor_mean_pool_bwd(int dtype, const void* dy, void* dx, long long R, int X, int C, void* stream);
+/* bias gradient db[n] += sum_m dy[m,n] */
+int valor_colsum(int dtype, const void* dy, long long ld, float* db, long long M, int N, void* stream);
+int valor_cast(int src_dtype, int dst_dtype, const void* src, void* dst, long long n, void* stream);
+int valor_strided_rows(int dtype, const void* src, long long sld, void* dst, long long dld, long long R, int C, int accumulate, void* stream);
+
+/* ---- losses ------------------------------------------------------------------------------------ */
+/* F.cross_entropy over the MLM head (pretrain.py:441-444); labels -1 ignored; acc = {sum, count} */
+int valor_xent_fwd(int dtype, const void* logits, long long ld, const long long* labels, float* lse, float* acc, float* loss, long long M, int V, void* stream);
+int valor_xent_bwd(int dtype, const void* logits, long long ld, const long long* labels, const float* lse, const float* acc, const float* gptr, float gmul, void* dlogits, long long ldd, long long M, int V, void* stream);
+/* weight softmax with -inf fill (pretrain.py:193-197) */
+int valor_masked_softmax_fwd(const float* w, const unsigned char* mask, float* ws, int R, int L, void* stream);
+int valor_masked_softmax_bwd(const float* ws, const float* dws, float* dw, int R, int L, void* stream);
+/* compute_fine_matrix_slice reductions (pretrain.py:200-209) over L = featA.featB^T [Na*T, Nb*Vt] */
+int valor_fine_reduce_fwd(const float* L, long long ldl, const unsigned char* mA, const float* wsA, const float* wsB, float* score, unsigned char* arg_v, unsigned char* arg_t, int Na, int Nb, int T, int Vt, int v0, int nv, void* stream);
+int valor_fine_reduce_bwd(const float* L, long long ldl, const unsigned char* mA, const float* wsA, const float* wsB, const float* dscore, const unsigned char* arg_v, const unsigned char* arg_t, float* dL, float* dwsA, float* dwsB, int Na, int Nb, int T, int Vt, int v0, int nv, void* stream);
+/* VALORModel.contrastive_loss (modeling.py:418-433) */
+int valor_contrastive_fwd(const float* S, const float* temp, float* row_lse, float* col_lse, float* loss, int N, void* stream);
+int valor_contrastive_bwd(const float* S, const float* temp, const float* row_lse, const float* col_lse, const float* gptr, float gmul, float* dS, float* dtemp, int N, void* stream);
+
+/* ---- optimizer step: optim/adamw.py:50-101 + clip_grad_norm_ (train_utils.py:359) ------------- */
+int valor_grad_sumsq(const float* g, long long n, float* out, void* stream);
+int valor_clip_coef(const float* sumsq, float max_norm, float* norm_out, void* stream);
+/* hyper = {lr, beta1, beta2, eps, weight_decay, step_size} on device; coef = clip coefficient or NULL */
+int valor_adamw(float* p, const float* g, float* m, float* v, void* p_lp, long long n, const float* hyper, const float* coef, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALOR_B200_H */

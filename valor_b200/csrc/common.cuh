@@ -1,0 +1,144 @@
+// valor_b200 — shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#define VALOR_DT_F32 0
+#define VALOR_DT_BF16 1
+
+namespace valor {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (C ABI returns int, message via valor_last_error) -----------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define VALOR_REQUIRE(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      valor::set_error(__VA_ARGS__);        \
+      return 1;                             \
+    }                                       \
+  } while (0)
+
+#define VALOR_CUDA(expr)                                                          \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      valor::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));           \
+      return 1;                                                                   \
+    }                                                                             \
+  } while (0)
+
+// ---- dtype helpers ---------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float ld_any(const void* p, int dtype, size_t i) {
+  return dtype == VALOR_DT_BF16 ? __bfloat162float(((const bf16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
+  if (dtype == VALOR_DT_BF16) ((bf16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+// ---- activations (reference: erf-GELU bert.py:52-57 / transformer.py:32-38 / nn.GELU;
+//      QuickGELU clip.py:167-169; ReLU pretrain.py:105) --------------------------------
+#define VALOR_ACT_NONE 0
+#define VALOR_ACT_GELU 1
+#define VALOR_ACT_QUICKGELU 2
+#define VALOR_ACT_RELU 3
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case VALOR_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case VALOR_ACT_QUICKGELU: return x / (1.0f + __expf(-1.702f * x));
+    case VALOR_ACT_RELU: return x > 0.f ? x : 0.f;
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_grad(float x, int act) {
+  switch (act) {
+    case VALOR_ACT_GELU: {
+      float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+      float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+      return cdf + x * pdf;
+    }
+    case VALOR_ACT_QUICKGELU: {
+      float s = 1.0f / (1.0f + __expf(-1.702f * x));
+      return s * (1.0f + 1.702f * x * (1.0f - s));
+    }
+    case VALOR_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    default: return 1.f;
+  }
+}
+
+// ---- warp / block reductions -----------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// blockDim.x multiple of 32, <= 1024. `sh` must hold 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sh[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- GEMM epilogue description (shared by the tcgen05 and SIMT kernels) -----------------
+struct GemmEpilogue {
+  const float* bias;     // [N] fp32 or null
+  const void* residual;  // [M,N] (ld = ldr), dtype = res_dtype, added AFTER activation
+  const void* act_aux;   // [M,N] pre-activation saved by the forward; out = acc * act'(aux)
+  void* preact_out;      // [M,N] optional: pre-activation (acc + bias) in out dtype
+  long long ldr, ld_aux, ld_pre;
+  int res_dtype, aux_dtype;
+  int act;               // VALOR_ACT_*
+  int out_dtype;         // VALOR_DT_*
+  int accumulate;        // 1: C += result (fp32 out only; atomic when split-K)
+  float alpha;           // scales the accumulator before bias
+};
+
+}  // namespace valor

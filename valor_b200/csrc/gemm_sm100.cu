@@ -1,0 +1,487 @@
+// valor_b200 — tcgen05 / TMEM / TMA GEMM with fused epilogues (sm_100a only).
+//
+//   C[M,N] (+)= epilogue( alpha * A[M,K] . B[N,K]^T )
+//
+// One kernel serves the three GEMM forms of every Linear on VALOR's hot path
+// (reference: nn.Linear / torch.matmul call sites):
+//   forward : A = x   [M,K]  K-major,   B = W  [N,K]  K-major
+//   dgrad   : A = dy  [M,N'] K-major,   B = W  stored [N',K'] -> MN-major (contract over N')
+//   wgrad   : A = dy  stored [M',N] -> MN-major, B = x stored [M',K] -> MN-major (contract M')
+//
+// Design: persistent, warp-specialised. warp0 = TMA producer (cp.async.bulk.tensor, 128B
+// swizzle), warp1 = single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 in,
+// fp32 accumulate in TMEM, 2 accumulator stages), warp2 = TMEM allocator, warps4-7 =
+// epilogue (tcgen05.ld 32x32b -> bias / activation / act-grad / residual -> 16B stores,
+// or red.global.add.v4.f32 for split-K weight-gradient accumulation).
+#include "common.cuh"
+#include <cudaTypedefs.h>
+
+namespace valor {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+static constexpr int UMMA_K = 16;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): 128B swizzle.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;  // version = 1 (Blackwell)
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias*/;
+};
+
+template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  void* __restrict__ Cptr, long long ldc, int M, int N, int K, int k_splits, int vec_ok,
+                  GemmEpilogue ep) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
+  float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = (kb_total + k_splits - 1) / k_splits;
+  const int total_work = m_blocks * n_blocks * k_splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n_blk = w % n_blocks;
+        const int rest = w / n_blocks;
+        const int ks = rest % k_splits;
+        const int m_blk = rest / k_splits;
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb0 + kb_per, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          if (A_KMAJOR) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(&tmA, &full_bar[stage], sa + j * (BLOCK_K * 128), m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+          }
+          if (B_KMAJOR) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(&tmB, &full_bar[stage], sb + j * (BLOCK_K * 128), n_blk * BLOCK_N + j * 64, kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
+                             ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int rest = w / n_blocks;
+        const int ks = rest % k_splits;
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb0 + kb_per, kb_total);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: advance 32 B inside the 128B swizzle row; SBO = 8 rows * 128 B.
+            // MN-major: 16 k-rows * 128 B; SBO = 1024 (8 k-rows), LBO = BLOCK_K*128 (next 64-wide MN atom).
+            const uint64_t adesc = A_KMAJOR ? make_smem_desc(sa + k * UMMA_K * 2, 0, 1024)
+                                            : make_smem_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024);
+            const uint64_t bdesc = B_KMAJOR ? make_smem_desc(sb + k * UMMA_K * 2, 0, 1024)
+                                            : make_smem_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024);
+            tcgen05_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) tcgen05_commit(&tmem_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may touch
+    const int et = threadIdx.x - 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int n_blk = w % n_blocks;
+      const int rest = w / n_blocks;
+      const int m_blk = rest / k_splits;
+      const int ks = rest % k_splits;
+      const int n0 = n_blk * BLOCK_N;
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      // stage the bias slice (only split 0 adds bias when split-K accumulates)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < BLOCK_N; i += 128) {
+        float b = 0.f;
+        if (ep.bias != nullptr && ks == 0 && n0 + i < N) b = ep.bias[n0 + i];
+        bias_s[i] = b;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < M && col0 < N) {
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 32 + j];
+          if (vec_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col >= N) break;
+              float* xg = x + g * 8;
+              if (ep.preact_out != nullptr) {
+                uint4 pk;
+                __nv_bfloat162* h = (__nv_bfloat162*)&pk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
+                *(uint4*)((bf16*)ep.preact_out + (size_t)row * ep.ld_pre + col) = pk;
+              }
+              if (ep.act_aux != nullptr) {
+                uint4 a = *(const uint4*)((const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col);
+                const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = __bfloat1622float2(h[j]);
+                  xg[2 * j] *= act_grad(f.x, ep.act);
+                  xg[2 * j + 1] *= act_grad(f.y, ep.act);
+                }
+              } else if (ep.act != VALOR_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
+              }
+              if (ep.residual != nullptr) {
+                uint4 r = *(const uint4*)((const bf16*)ep.residual + (size_t)row * ep.ldr + col);
+                const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = __bfloat1622float2(h[j]);
+                  xg[2 * j] += f.x;
+                  xg[2 * j + 1] += f.y;
+                }
+              }
+              if (ep.out_dtype == VALOR_DT_BF16) {
+                uint4 pk;
+                __nv_bfloat162* h = (__nv_bfloat162*)&pk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
+                *(uint4*)((bf16*)Cptr + (size_t)row * ldc + col) = pk;
+              } else {
+                float* dst = (float*)Cptr + (size_t)row * ldc + col;
+                if (ep.accumulate) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xg[0]), "f"(xg[1]),
+                               "f"(xg[2]), "f"(xg[3])
+                               : "memory");
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(xg[4]), "f"(xg[5]),
+                               "f"(xg[6]), "f"(xg[7])
+                               : "memory");
+                } else {
+                  *(float4*)dst = make_float4(xg[0], xg[1], xg[2], xg[3]);
+                  *(float4*)(dst + 4) = make_float4(xg[4], xg[5], xg[6], xg[7]);
+                }
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col >= N) break;
+              float y = x[j];
+              if (ep.preact_out != nullptr) ((bf16*)ep.preact_out)[(size_t)row * ep.ld_pre + col] = __float2bfloat16_rn(y);
+              if (ep.act_aux != nullptr)
+                y *= act_grad(__bfloat162float(((const bf16*)ep.act_aux)[(size_t)row * ep.ld_aux + col]), ep.act);
+              else
+                y = act_fwd(y, ep.act);
+              if (ep.residual != nullptr) y += __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col]);
+              if (ep.out_dtype == VALOR_DT_BF16) {
+                ((bf16*)Cptr)[(size_t)row * ldc + col] = __float2bfloat16_rn(y);
+              } else {
+                float* dst = (float*)Cptr + (size_t)row * ldc + col;
+                if (ep.accumulate) atomicAdd(dst, y);
+                else *dst = y;
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor, `inner` contiguous, row pitch `ld` elements; box = {64, box_outer}, 128B swizzle.
+static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  auto fn = get_encode_fn();
+  VALOR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VALOR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu ptr=%p", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, ptr);
+  return 0;
+}
+
+template <int BN, bool AK, bool BK>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, void* C, long long ldc, int M, int N, int K,
+                      int k_splits, int vec_ok, const GemmEpilogue& ep, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_sm100_kernel<BN, AK, BK>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep);
+  return check_launch("gemm_sm100_kernel");
+}
+
+template <bool AK, bool BK>
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, long long ldc, int M, int N, int K,
+                     int k_splits, int vec_ok, const GemmEpilogue& ep, int grid, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_cfg<64, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+    case 128: return launch_cfg<128, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+    case 192: return launch_cfg<192, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+    default: return launch_cfg<256, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+  }
+}
+
+// Eligibility: bf16 operands, 16-byte aligned base pointers and row pitches.
+bool gemm_sm100_eligible(const void* A, const void* B, long long lda, long long ldb, int M, int N, int K) {
+  if (((uintptr_t)A | (uintptr_t)B) & 15) return false;
+  if ((lda % 8) || (ldb % 8)) return false;
+  if (M < 1 || N < 8 || K < 8) return false;
+  return true;
+}
+
+int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor, void* C,
+               long long ldc, int M, int N, int K, const GemmEpilogue& ep, int force_bn, int force_splits,
+               cudaStream_t st) {
+  VALOR_REQUIRE(gemm_sm100_eligible(A, B, lda, ldb, M, N, K), "gemm_sm100: operands not TMA-eligible");
+  VALOR_REQUIRE(!ep.accumulate || ep.out_dtype == VALOR_DT_F32, "gemm_sm100: accumulate needs fp32 output");
+  VALOR_REQUIRE(ep.residual == nullptr || ep.res_dtype == VALOR_DT_BF16, "gemm_sm100: residual must be bf16");
+  VALOR_REQUIRE(ep.act_aux == nullptr || ep.aux_dtype == VALOR_DT_BF16, "gemm_sm100: act_aux must be bf16");
+  const int sms = num_sms();
+  const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  // ---- BLOCK_N: least padding waste, then enough tiles to fill the machine
+  int bn = 256;
+  if (force_bn) {
+    bn = force_bn;
+  } else {
+    const int cands[3] = {256, 192, 128};
+    long best = -1;
+    for (int i = 0; i < 3; ++i) {
+      long waste = (long)((N + cands[i] - 1) / cands[i]) * cands[i] - N;
+      if (best < 0 || waste < best) { best = waste; bn = cands[i]; }
+    }
+    if (N <= 64) bn = 64;
+    while (bn > 64 && (long)m_blocks * ((N + bn - 1) / bn) < sms && !ep.accumulate) bn = (bn == 192) ? 128 : bn / 2;
+  }
+  const int n_blocks = (N + bn - 1) / bn;
+  const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  int k_splits = 1;
+  if (force_splits > 0) {
+    k_splits = force_splits;
+  } else if (ep.accumulate && ep.out_dtype == VALOR_DT_F32) {
+    const long tiles = (long)m_blocks * n_blocks;
+    if (tiles < sms) {
+      k_splits = (int)((2L * sms + tiles - 1) / tiles);
+      int max_splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+      if (k_splits > max_splits) k_splits = max_splits;
+    }
+  }
+  if (k_splits > kb_total) k_splits = kb_total;
+  if (k_splits < 1) k_splits = 1;
+  {  // every split must own >= 1 k-block
+    int per = (kb_total + k_splits - 1) / k_splits;
+    k_splits = (kb_total + per - 1) / per;
+  }
+  VALOR_REQUIRE(k_splits == 1 || ep.accumulate, "gemm_sm100: split-K requires accumulate");
+
+  CUtensorMap ta, tb;
+  if (a_kmajor) { if (make_tmap(&ta, A, K, M, lda, BLOCK_M)) return 1; }
+  else          { if (make_tmap(&ta, A, M, K, lda, BLOCK_K)) return 1; }
+  if (b_kmajor) { if (make_tmap(&tb, B, K, N, ldb, bn)) return 1; }
+  else          { if (make_tmap(&tb, B, N, K, ldb, BLOCK_K)) return 1; }
+
+  int vec_ok = (N % 8 == 0) && (ldc % 8 == 0) && (((uintptr_t)C & 15) == 0);
+  if (ep.residual) vec_ok = vec_ok && (ep.ldr % 8 == 0) && (((uintptr_t)ep.residual & 15) == 0);
+  if (ep.act_aux) vec_ok = vec_ok && (ep.ld_aux % 8 == 0) && (((uintptr_t)ep.act_aux & 15) == 0);
+  if (ep.preact_out) vec_ok = vec_ok && (ep.ld_pre % 8 == 0) && (((uintptr_t)ep.preact_out & 15) == 0);
+
+  const long total = (long)m_blocks * n_blocks * k_splits;
+  const int grid = (int)(total < sms ? total : sms);
+  if (a_kmajor && b_kmajor) return launch_bn<true, true>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+  if (a_kmajor && !b_kmajor) return launch_bn<true, false>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+  if (!a_kmajor && b_kmajor) return launch_bn<false, true>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+  return launch_bn<false, false>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+}
+
+}  // namespace valor

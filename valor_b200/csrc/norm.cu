@@ -1,0 +1,270 @@
+// valor_b200 — row-wise normalisation kernels (HBM-bound; one warp per row, 8-byte/16-byte
+// vector accesses, fp32 statistics).
+//   layernorm : apex FusedLayerNorm (apex/csrc/layer_norm_cuda_kernel.cu cuApplyLayerNorm /
+//               cuComputeGradInput / cuComputeGradGammaBeta) and nn.LayerNorm in Swin
+//   l2norm    : F.normalize(dim=-1) on the contrastive features (pretrain.py:276,283,289)
+#include "common.cuh"
+
+namespace valor {
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *(const float4*)p; }
+  __device__ __forceinline__ void store(float* p) const { *(float4*)p = v; }
+  __device__ __forceinline__ void get(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  __device__ __forceinline__ void set(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec4<bf16> {
+  uint2 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *(const uint2*)p; }
+  __device__ __forceinline__ void store(bf16* p) const { *(uint2*)p = v; }
+  __device__ __forceinline__ void get(float* f) const {
+    const __nv_bfloat162* h = (const __nv_bfloat162*)&v;
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  __device__ __forceinline__ void set(const float* f) {
+    __nv_bfloat162* h = (__nv_bfloat162*)&v;
+    h[0] = __floats2bfloat162_rn(f[0], f[1]);
+    h[1] = __floats2bfloat162_rn(f[2], f[3]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma + beta ; saves mean, rstd (fp32)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int N,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T* xr = x + row * N;
+  T* yr = y + row * N;
+  const int nv = N >> 2;
+  float s = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    Vec4<T> v; v.load(xr + 4 * i);
+    float f[4]; v.get(f);
+    s += f[0] + f[1] + f[2] + f[3];
+  }
+  const float mean = warp_sum(s) / N;
+  float ss = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    Vec4<T> v; v.load(xr + 4 * i);
+    float f[4]; v.get(f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float d = f[e] - mean; ss += d * d; }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / N + eps);
+  for (int i = lane; i < nv; i += 32) {
+    Vec4<T> v; v.load(xr + 4 * i);
+    float f[4]; v.get(f);
+    const float4 g = *(const float4*)(gamma + 4 * i);
+    const float4 b = *(const float4*)(beta + 4 * i);
+    f[0] = (f[0] - mean) * rstd * g.x + b.x;
+    f[1] = (f[1] - mean) * rstd * g.y + b.y;
+    f[2] = (f[2] - mean) * rstd * g.z + b.z;
+    f[3] = (f[3] - mean) * rstd * g.w + b.w;
+    v.set(f); v.store(yr + 4 * i);
+  }
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm backward: dx per row; dgamma/dbeta accumulated per lane in registers over the
+// rows a warp visits (each lane owns the same columns on every row), then reduced through
+// shared memory and flushed with one atomicAdd per column per CTA into fp32 gradients.
+// ---------------------------------------------------------------------------------------
+template <typename T, int VPL /* float4-groups per lane; N == VPL*128 */>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int N) {
+  extern __shared__ float sh[];  // [2][N]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float ag[VPL][4], ab[VPL][4];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
+  for (long long row = (long long)blockIdx.x * nwarp + warp; row < M; row += (long long)gridDim.x * nwarp) {
+    const T* dyr = dy + row * N;
+    const T* xr = x + row * N;
+    const float mu = mean[row], rs = rstd[row];
+    float fdy[VPL][4], fxh[VPL][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      Vec4<T> a, b; a.load(dyr + c); b.load(xr + c);
+      a.get(fdy[k]); b.get(fxh[k]);
+      const float4 g = *(const float4*)(gamma + c);
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        fxh[k][e] = (fxh[k][e] - mu) * rs;
+        ag[k][e] += fdy[k][e] * fxh[k][e];
+        ab[k][e] += fdy[k][e];
+        fdy[k][e] *= gg[e];  // dy * gamma
+        s1 += fdy[k][e];
+        s2 += fdy[k][e] * fxh[k][e];
+      }
+    }
+    s1 = warp_sum(s1) / N;
+    s2 = warp_sum(s2) / N;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (fdy[k][e] - s1 - fxh[k][e] * s2) * rs;
+      Vec4<T> v; v.set(o); v.store(dx + row * N + c);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = (k * 32 + lane) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(&sh[c + e], ag[k][e]);
+      atomicAdd(&sh[N + c + e], ab[k][e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[i], sh[i]);
+    if (dbeta) atomicAdd(&dbeta[i], sh[N + i]);
+  }
+}
+
+// generic-N fallback (N % 4 == 0): re-reads the row, shared-memory atomics for dgamma/dbeta
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_generic_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                             const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int N) {
+  extern __shared__ float sh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  for (long long row = (long long)blockIdx.x * nwarp + warp; row < M; row += (long long)gridDim.x * nwarp) {
+    const T* dyr = dy + row * N;
+    const T* xr = x + row * N;
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      const float d = to_f(dyr[c]), xh = (to_f(xr[c]) - mu) * rs, g = gamma[c];
+      atomicAdd(&sh[c], d * xh);
+      atomicAdd(&sh[N + c], d);
+      s1 += d * g;
+      s2 += d * g * xh;
+    }
+    s1 = warp_sum(s1) / N;
+    s2 = warp_sum(s2) / N;
+    for (int c = lane; c < N; c += 32) {
+      const float d = to_f(dyr[c]) * gamma[c], xh = (to_f(xr[c]) - mu) * rs;
+      dx[row * N + c] = from_f<T>((d - s1 - xh * s2) * rs);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[i], sh[i]);
+    if (dbeta) atomicAdd(&dbeta[i], sh[N + i]);
+  }
+}
+
+template <typename T>
+static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                           void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
+  long long want = (M + 7) / 8;
+  int grid = (int)(want < (long long)num_sms() * 4 ? want : (long long)num_sms() * 4);
+  if (grid < 1) grid = 1;
+  size_t smem = (size_t)2 * N * sizeof(float);
+#define LN_BWD_CASE(V)                                                                                          \
+  case V * 128:                                                                                                 \
+    layernorm_bwd_kernel<T, V><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,   \
+                                                         dgamma, dbeta, M, N);                                  \
+    break;
+  switch (N) {
+    LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(4) LN_BWD_CASE(6) LN_BWD_CASE(8) LN_BWD_CASE(16)
+    default:
+      layernorm_bwd_generic_kernel<T><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
+                                                                dgamma, dbeta, M, N);
+  }
+#undef LN_BWD_CASE
+  return check_launch("layernorm_bwd_kernel");
+}
+
+int layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                  long long M, int N, float eps, cudaStream_t st) {
+  VALOR_REQUIRE(N % 4 == 0, "layernorm: N=%d must be a multiple of 4", N);
+  const long long blocks = (M + 7) / 8;
+  VALOR_REQUIRE(blocks < 2147483647LL, "layernorm: too many rows");
+  if (M == 0) return 0;
+  if (dtype == VALOR_DT_F32)
+    layernorm_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, N, eps);
+  else
+    layernorm_fwd_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, N, eps);
+  return check_launch("layernorm_fwd_kernel");
+}
+
+int layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                  void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
+  VALOR_REQUIRE(N % 4 == 0, "layernorm: N=%d must be a multiple of 4", N);
+  if (M == 0) return 0;
+  if (dtype == VALOR_DT_F32) return ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, N, st);
+  return ln_bwd_dispatch<bf16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, N, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// L2 normalise: y = x / max(||x||, 1e-12) ; bwd dx = (dy - y (y.dy)) / max(||x||,1e-12)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void l2norm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ nrm, long long M, int N) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float s = 0.f;
+  for (int c = lane; c < N; c += 32) { float v = to_f(x[row * N + c]); s += v * v; }
+  const float n = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+  for (int c = lane; c < N; c += 32) y[row * N + c] = from_f<T>(to_f(x[row * N + c]) / n);
+  if (lane == 0) nrm[row] = n;
+}
+template <typename T>
+__global__ void l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ nrm,
+                                  T* __restrict__ dx, long long M, int N) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float n = nrm[row];
+  float s = 0.f;
+  for (int c = lane; c < N; c += 32) s += to_f(dy[row * N + c]) * to_f(x[row * N + c]) / n;
+  s = warp_sum(s);
+  for (int c = lane; c < N; c += 32) {
+    const float yv = to_f(x[row * N + c]) / n;
+    dx[row * N + c] = from_f<T>((to_f(dy[row * N + c]) - yv * s) / n);
+  }
+}
+
+int l2norm_fwd(int dtype, const void* x, void* y, float* nrm, long long M, int N, cudaStream_t st) {
+  if (M == 0) return 0;
+  unsigned blocks = (unsigned)((M + 7) / 8);
+  if (dtype == VALOR_DT_F32) l2norm_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, nrm, M, N);
+  else l2norm_fwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, nrm, M, N);
+  return check_launch("l2norm_fwd_kernel");
+}
+int l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm, void* dx, long long M, int N, cudaStream_t st) {
+  if (M == 0) return 0;
+  unsigned blocks = (unsigned)((M + 7) / 8);
+  if (dtype == VALOR_DT_F32) l2norm_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)x, nrm, (float*)dx, M, N);
+  else l2norm_bwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, nrm, (bf16*)dx, M, N);
+  return check_launch("l2norm_bwd_kernel");
+}
+
+}  // namespace valor
