@@ -133,7 +133,10 @@ int valor_mean_pool_fwd(int dtype, const void* x, void* y, long long R, int X, i
 int valor_mean_pool_bwd(int dtype, const void* dy, void* dx, long long R, int X, int C, void* stream);
 /* bias gradient db[n] += sum_m dy[m,n] */
 int valor_colsum(int dtype, const void* dy, long long ld, float* db, long long M, int N, void* stream);
-int valor_cast(int src_dtype, int dst_dtype, const void* src, void* dst, long long n, void* stream);
+/* dst[r,c] = cast(src[r,c]) over [R,C] with row pitches (flat: R=1) */
+int valor_cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, void* dst, long long dld, long long R, long long C, void* stream);
+/* dh = dy * act'(h): gradient through GELU / QuickGELU / ReLU where it cannot ride a GEMM epilogue */
+int valor_act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, void* stream);
 int valor_strided_rows(int dtype, const void* src, long long sld, void* dst, long long dld, long long R, int C, int accumulate, void* stream);
 
 /* ---- losses ------------------------------------------------------------------------------------ */

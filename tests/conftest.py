@@ -21,3 +21,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def cpu_kernels(monkeypatch):
+    """Install tests/cpu_backend.py over valor_b200.kernels (host-logic tests only)."""
+    import types
+    from tests import cpu_backend
+    import valor_b200.kernels as K
+    for name in dir(cpu_backend):
+        obj = getattr(cpu_backend, name)
+        if isinstance(obj, types.FunctionType) and not name.startswith("_"):
+            monkeypatch.setattr(K, name, obj)
+    return K

@@ -45,7 +45,8 @@ int patch_merge(int, const void*, void*, long long, int, int, int, int, cudaStre
 int mean_pool_fwd(int, const void*, void*, long long, int, int, cudaStream_t);
 int mean_pool_bwd(int, const void*, void*, long long, int, int, cudaStream_t);
 int colsum(int, const void*, long long, float*, long long, int, cudaStream_t);
-int cast(int, int, const void*, void*, long long, cudaStream_t);
+int cast2d(int, int, const void*, long long, void*, long long, long long, long long, cudaStream_t);
+int act_bwd(int, const void*, const void*, void*, long long, int, cudaStream_t);
 int strided_rows(int, const void*, long long, void*, long long, long long, int, int, cudaStream_t);
 int xent_fwd(int, const void*, long long, const long long*, float*, float*, float*, long long, int, cudaStream_t);
 int xent_bwd(int, const void*, long long, const long long*, const float*, const float*, const float*, float, void*, long long, long long, int, cudaStream_t);
@@ -209,8 +210,11 @@ int valor_mean_pool_bwd(int dtype, const void* dy, void* dx, long long R, int X,
 int valor_colsum(int dtype, const void* dy, long long ld, float* db, long long M, int N, void* stream) {
   return colsum(dtype, dy, ld, db, M, N, ST);
 }
-int valor_cast(int src_dtype, int dst_dtype, const void* src, void* dst, long long n, void* stream) {
-  return cast(src_dtype, dst_dtype, src, dst, n, ST);
+int valor_cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, void* dst, long long dld, long long R, long long C, void* stream) {
+  return cast2d(src_dtype, dst_dtype, src, sld, dst, dld, R, C, ST);
+}
+int valor_act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, void* stream) {
+  return act_bwd(dtype, dy, h, dh, n, act, ST);
 }
 int valor_strided_rows(int dtype, const void* src, long long sld, void* dst, long long dld, long long R, int C, int accumulate, void* stream) {
   return strided_rows(dtype, src, sld, dst, dld, R, C, accumulate, ST);

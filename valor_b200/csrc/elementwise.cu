@@ -369,36 +369,43 @@ int colsum(int dtype, const void* dy, long long ld, float* db, long long M, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// casts and strided row copies
+// 2-D strided dtype casts, activation gradient, strided row copies
 // ---------------------------------------------------------------------------------------
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
-  const long long n4 = n / 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = ((const float4*)src)[i];
-    uint2 o;
-    __nv_bfloat162* h = (__nv_bfloat162*)&o;
-    h[0] = __floats2bfloat162_rn(v.x, v.y);
-    h[1] = __floats2bfloat162_rn(v.z, v.w);
-    ((uint2*)dst)[i] = o;
+template <typename TS, typename TD>
+__global__ void cast2d_kernel(const TS* __restrict__ src, long long sld, TD* __restrict__ dst, long long dld, long long R, long long C) {
+  const long long total = R * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / C, c = idx % C;
+    dst[r * dld + c] = from_f<TD>(to_f(src[r * sld + c]));
   }
-  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16_rn(src[i]);
 }
-__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = __bfloat162float(src[i]);
-}
-int cast(int src_dtype, int dst_dtype, const void* src, void* dst, long long n, cudaStream_t st) {
-  if (n == 0) return 0;
-  VALOR_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "cast: pointers must be 16-byte aligned");
-  unsigned g = grid_for(n / 4 + 1, 256);
+int cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, void* dst, long long dld, long long R, long long C, cudaStream_t st) {
+  if (R * C == 0) return 0;
+  unsigned g = grid_for(R * C, 256);
   if (src_dtype == VALOR_DT_F32 && dst_dtype == VALOR_DT_BF16)
-    cast_f32_bf16_kernel<<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+    cast2d_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, sld, (bf16*)dst, dld, R, C);
   else if (src_dtype == VALOR_DT_BF16 && dst_dtype == VALOR_DT_F32)
-    cast_bf16_f32_kernel<<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+    cast2d_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, sld, (float*)dst, dld, R, C);
+  else if (src_dtype == VALOR_DT_F32 && dst_dtype == VALOR_DT_F32)
+    cast2d_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, sld, (float*)dst, dld, R, C);
   else
-    VALOR_REQUIRE(false, "cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
-  return check_launch("cast_kernel");
+    cast2d_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, sld, (bf16*)dst, dld, R, C);
+  return check_launch("cast2d_kernel");
+}
+
+// dh = dy * act'(h)   (flat, same dtype)
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, T* __restrict__ dh, long long n, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dh[i] = from_f<T>(to_f(dy[i]) * act_grad(to_f(h[i]), act));
+}
+int act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, cudaStream_t st) {
+  if (n == 0) return 0;
+  unsigned g = grid_for(n, 256);
+  if (dtype == VALOR_DT_F32) act_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)dy, (const float*)h, (float*)dh, n, act);
+  else act_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dy, (const bf16*)h, (bf16*)dh, n, act);
+  return check_launch("act_bwd_kernel");
 }
 
 // dst[r*dld + c] (=|+=) src[r*sld + c]   — cls-token select (modeling.py:399) and its gradient

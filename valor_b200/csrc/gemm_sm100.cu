@@ -263,21 +263,31 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 32 + j];
-          if (vec_ok) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col >= N) break;
-              float* xg = x + g * 8;
-              if (ep.preact_out != nullptr) {
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= N) break;
+            float* xg = x + g * 8;
+            const bool full = vec_ok && (col + 8 <= N);
+            const int nvalid = (N - col) < 8 ? (N - col) : 8;
+            // ---- pre-activation side output
+            if (ep.preact_out != nullptr) {
+              bf16* dst = (bf16*)ep.preact_out + (size_t)row * ep.ld_pre + col;
+              if (full) {
                 uint4 pk;
                 __nv_bfloat162* h = (__nv_bfloat162*)&pk;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
-                *(uint4*)((bf16*)ep.preact_out + (size_t)row * ep.ld_pre + col) = pk;
+                *(uint4*)dst = pk;
+              } else {
+                for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(xg[j]);
               }
-              if (ep.act_aux != nullptr) {
-                uint4 a = *(const uint4*)((const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col);
+            }
+            // ---- activation or activation gradient
+            if (ep.act_aux != nullptr) {
+              const bf16* src = (const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col;
+              if (full) {
+                uint4 a = *(const uint4*)src;
                 const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -285,12 +295,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   xg[2 * j] *= act_grad(f.x, ep.act);
                   xg[2 * j + 1] *= act_grad(f.y, ep.act);
                 }
-              } else if (ep.act != VALOR_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
+              } else {
+                for (int j = 0; j < nvalid; ++j) xg[j] *= act_grad(__bfloat162float(src[j]), ep.act);
               }
-              if (ep.residual != nullptr) {
-                uint4 r = *(const uint4*)((const bf16*)ep.residual + (size_t)row * ep.ldr + col);
+            } else if (ep.act != VALOR_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
+            }
+            // ---- residual
+            if (ep.residual != nullptr) {
+              const bf16* src = (const bf16*)ep.residual + (size_t)row * ep.ldr + col;
+              if (full) {
+                uint4 r = *(const uint4*)src;
                 const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -298,15 +314,25 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   xg[2 * j] += f.x;
                   xg[2 * j + 1] += f.y;
                 }
+              } else {
+                for (int j = 0; j < nvalid; ++j) xg[j] += __bfloat162float(src[j]);
               }
-              if (ep.out_dtype == VALOR_DT_BF16) {
+            }
+            // ---- store
+            if (ep.out_dtype == VALOR_DT_BF16) {
+              bf16* dst = (bf16*)Cptr + (size_t)row * ldc + col;
+              if (full) {
                 uint4 pk;
                 __nv_bfloat162* h = (__nv_bfloat162*)&pk;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
-                *(uint4*)((bf16*)Cptr + (size_t)row * ldc + col) = pk;
+                *(uint4*)dst = pk;
               } else {
-                float* dst = (float*)Cptr + (size_t)row * ldc + col;
+                for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(xg[j]);
+              }
+            } else {
+              float* dst = (float*)Cptr + (size_t)row * ldc + col;
+              if (full && (ldc % 4 == 0)) {
                 if (ep.accumulate) {
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xg[0]), "f"(xg[1]),
                                "f"(xg[2]), "f"(xg[3])
@@ -318,25 +344,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   *(float4*)dst = make_float4(xg[0], xg[1], xg[2], xg[3]);
                   *(float4*)(dst + 4) = make_float4(xg[4], xg[5], xg[6], xg[7]);
                 }
-              }
-            }
-          } else {
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              if (col >= N) break;
-              float y = x[j];
-              if (ep.preact_out != nullptr) ((bf16*)ep.preact_out)[(size_t)row * ep.ld_pre + col] = __float2bfloat16_rn(y);
-              if (ep.act_aux != nullptr)
-                y *= act_grad(__bfloat162float(((const bf16*)ep.act_aux)[(size_t)row * ep.ld_aux + col]), ep.act);
-              else
-                y = act_fwd(y, ep.act);
-              if (ep.residual != nullptr) y += __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col]);
-              if (ep.out_dtype == VALOR_DT_BF16) {
-                ((bf16*)Cptr)[(size_t)row * ldc + col] = __float2bfloat16_rn(y);
               } else {
-                float* dst = (float*)Cptr + (size_t)row * ldc + col;
-                if (ep.accumulate) atomicAdd(dst, y);
-                else *dst = y;
+                for (int j = 0; j < nvalid; ++j) {
+                  if (ep.accumulate) atomicAdd(dst + j, xg[j]);
+                  else dst[j] = xg[j];
+                }
               }
             }
           }
@@ -471,7 +483,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   if (b_kmajor) { if (make_tmap(&tb, B, K, N, ldb, bn)) return 1; }
   else          { if (make_tmap(&tb, B, N, K, ldb, BLOCK_K)) return 1; }
 
-  int vec_ok = (N % 8 == 0) && (ldc % 8 == 0) && (((uintptr_t)C & 15) == 0);
+  int vec_ok = (ldc % 8 == 0) && (((uintptr_t)C & 15) == 0);
   if (ep.residual) vec_ok = vec_ok && (ep.ldr % 8 == 0) && (((uintptr_t)ep.residual & 15) == 0);
   if (ep.act_aux) vec_ok = vec_ok && (ep.ld_aux % 8 == 0) && (((uintptr_t)ep.act_aux & 15) == 0);
   if (ep.preact_out) vec_ok = vec_ok && (ep.ld_pre % 8 == 0) && (((uintptr_t)ep.preact_out & 15) == 0);

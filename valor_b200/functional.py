@@ -1,0 +1,437 @@
+"""Autograd nodes of the hot path.  Each node is a thin composition of C-ABI kernels
+(valor_b200.kernels); the backward formulas are written by hand and the parameter gradients
+are accumulated straight into the flat fp32 gradient arena (`param.main_grad`, see
+params.ParamStore) by the weight-gradient GEMMs — autograd only orders the nodes.
+"""
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+
+
+class Lin:
+    """A (possibly fused) linear layer's buffers: low-precision weight view [N,K], fp32
+    gradient view, fp32 bias + its gradient."""
+    __slots__ = ("w", "w_grad", "b", "b_grad")
+
+    def __init__(self, w, w_grad, b=None, b_grad=None):
+        self.w, self.w_grad, self.b, self.b_grad = w, w_grad, b, b_grad
+
+
+def lin_of(weight, bias=None):
+    """Lin for one nn.Parameter pair attached to a ParamStore."""
+    return Lin(weight.lp, weight.main_grad, None if bias is None else bias.data,
+               None if bias is None else bias.main_grad)
+
+
+def fused_lin(weights, biases=None):
+    """Lin over parameters laid out back-to-back in the arenas (q|k|v packs).  The reference keeps
+    separate query/key/value Parameters (bert.py:233-235, transformer.py:109); the arena places
+    them adjacently so one GEMM serves all three without renaming any state-dict key."""
+    def cat_view(ts):
+        t0 = ts[0]
+        n = sum(t.shape[0] for t in ts)
+        ptr = t0.data_ptr()
+        for t in ts:
+            assert t.data_ptr() == ptr and t.is_contiguous(), "parameters are not adjacent in the arena"
+            ptr += t.numel() * t.element_size()
+        return t0.as_strided((n,) + tuple(t0.shape[1:]), t0.stride())
+
+    w = cat_view([p.lp for p in weights])
+    wg = cat_view([p.main_grad for p in weights])
+    if biases is None:
+        return Lin(w, wg)
+    return Lin(w, wg, cat_view([p.data for p in biases]), cat_view([p.main_grad for p in biases]))
+
+
+def _wgrad(lin, dy, x):
+    if lin.w_grad is not None:
+        K.gemm(dy, x, a_kmajor=False, b_kmajor=False, out=lin.w_grad, accumulate=True)
+    if lin.b_grad is not None:
+        K.colsum(dy, lin.b_grad)
+
+
+class LinearFn(Function):
+    """y = act(x W^T + b) + residual    (nn.Linear + activation + residual add in one GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, lin, act, residual, out_dtype, anchor):
+        x = x.contiguous()
+        N = lin.w.shape[0]
+        out = None
+        if N % 8 and N > 64 and act == K.ACT_NONE:
+            # odd-width outputs (the 30522-wide vocabulary) get a row pitch padded to 8 elements so
+            # the 16-byte epilogue stores and the TMA descriptors of the backward GEMMs stay aligned
+            out = torch.empty(x.shape[0], (N + 7) // 8 * 8, device=x.device, dtype=out_dtype or x.dtype)[:, :N]
+        if act != K.ACT_NONE:
+            y, h = K.gemm(x, lin.w, bias=lin.b, act=act, residual=residual, want_preact=True, out_dtype=out_dtype)
+        else:
+            y, h = K.gemm(x, lin.w, bias=lin.b, residual=residual, out_dtype=out_dtype, out=out), None
+        ctx.save_for_backward(x, h)
+        ctx.lin, ctx.act, ctx.has_res = lin, act, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, h = ctx.saved_tensors
+        lin = ctx.lin
+        if not (dy.dim() == 2 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0):
+            dy = dy.contiguous()
+        dres = dy if ctx.has_res else None
+        if dy.dtype != x.dtype:  # fp32 head outputs feeding low-precision operands
+            t = torch.empty(dy.shape, device=dy.device, dtype=x.dtype)
+            K.cast2d(dy, t)
+            dy_lp = t
+        else:
+            dy_lp = dy
+        dh = K.act_bwd(dy_lp, h, ctx.act) if h is not None else dy_lp
+        _wgrad(lin, dh, x)
+        dx = K.gemm(dh, lin.w, b_kmajor=False) if ctx.needs_input_grad[0] else None
+        return dx, None, None, dres, None, None
+
+
+def linear(x, lin, act=K.ACT_NONE, residual=None, out_dtype=None, anchor=None):
+    return LinearFn.apply(x, lin, act, residual, out_dtype, anchor)
+
+
+class MlpFn(Function):
+    """y = W2 act(W1 x + b1) + b2 + residual — Swin Mlp (videoswin.py:67-73), AST FeedForward
+    (transformer.py:141-142), BERT intermediate+output dense (bert.py:403-419).  The activation
+    gradient rides the fc2-dgrad GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, lin1, lin2, act, residual):
+        x = x.contiguous()
+        a, h = K.gemm(x, lin1.w, bias=lin1.b, act=act, want_preact=True)
+        y = K.gemm(a, lin2.w, bias=lin2.b, residual=residual)
+        ctx.save_for_backward(x, h, a)
+        ctx.l1, ctx.l2, ctx.act, ctx.has_res = lin1, lin2, act, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, h, a = ctx.saved_tensors
+        dy = dy.contiguous()
+        _wgrad(ctx.l2, dy, a)
+        dh = K.gemm(dy, ctx.l2.w, b_kmajor=False, act_aux=h, act=ctx.act)
+        _wgrad(ctx.l1, dh, x)
+        dx = K.gemm(dh, ctx.l1.w, b_kmajor=False) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, (dy if ctx.has_res else None)
+
+
+def mlp(x, lin1, lin2, act, residual=None):
+    return MlpFn.apply(x, lin1, lin2, act, residual)
+
+
+class LN:
+    __slots__ = ("g", "b", "g_grad", "b_grad", "eps")
+
+    def __init__(self, weight, bias, eps):
+        self.g, self.b, self.g_grad, self.b_grad, self.eps = weight.data, bias.data, weight.main_grad, bias.main_grad, eps
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, ln):
+        x = x.contiguous()
+        y, mean, rstd = K.layernorm_fwd(x, ln.g, ln.b, ln.eps)
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.ln = ln
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        ln = ctx.ln
+        return K.layernorm_bwd(dy, x, ln.g, mean, rstd, ln.g_grad, ln.b_grad), None
+
+
+def layer_norm(x, ln):
+    return LayerNormFn.apply(x, ln)
+
+
+class WindowAttnFn(Function):
+    """WindowAttention3D core on the natural token order (see include/valor_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, qkv, table, dtable, geom):
+        grid, win, shift, cfg_win, heads, hd, scale = geom
+        o, lse = K.window_attn_fwd(qkv, table, grid, win, shift, cfg_win, heads, hd, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.table, ctx.dtable, ctx.geom = table, dtable, geom
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        grid, win, shift, cfg_win, heads, hd, scale = ctx.geom
+        dqkv = K.window_attn_bwd(qkv, o, do, lse, ctx.table, ctx.dtable, grid, win, shift, cfg_win, heads, hd, scale)
+        return dqkv, None, None, None
+
+
+def window_attention(qkv, table_param, geom):
+    return WindowAttnFn.apply(qkv, table_param.data, table_param.main_grad, geom)
+
+
+class SelfAttnFn(Function):
+    """softmax(q k^T * scale + mask) v over a fused [rows, 3*Hd] q|k|v buffer."""
+
+    @staticmethod
+    def forward(ctx, qkv, spec):
+        Hd = spec["H"] * spec["hd"]
+        o, lse = K.mha_fwd(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], spec["P"], spec["H"], spec["hd"],
+                           spec["Nq"], spec["max_nk"], spec["scale"], key_valid=spec.get("key_valid"),
+                           causal=spec.get("causal"))
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.spec = spec
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        s = ctx.spec
+        Hd = s["H"] * s["hd"]
+        dqkv = torch.empty_like(qkv)
+        dkv = K.mha_bwd(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], o, do, lse, dqkv[:, :Hd], s["P"], s["H"],
+                        s["hd"], s["Nq"], s["max_nk"], s["scale"], key_valid=s.get("key_valid"), causal=s.get("causal"))
+        K.cast2d(dkv, dqkv[:, Hd:])
+        return dqkv, None
+
+
+class CrossAttnFn(Function):
+    """BertCrossAttention core (bert.py:314-340): q [rows,Hd]; kv [B*S, 2*Hd] (k|v) shared by
+    every pass of a sample through (kv_row0, kv_len) ranges; no mask (bert.py:327)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, spec):
+        Hd = spec["H"] * spec["hd"]
+        q = q.contiguous()
+        o, lse = K.mha_fwd(q, kv[:, :Hd], kv[:, Hd:], spec["P"], spec["H"], spec["hd"], spec["Nq"], spec["max_nk"],
+                           spec["scale"], kv_row0=spec["kv_row0"], kv_len=spec["kv_len"])
+        ctx.save_for_backward(q, kv, o, lse)
+        ctx.spec = spec
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, o, lse = ctx.saved_tensors
+        s = ctx.spec
+        Hd = s["H"] * s["hd"]
+        dq = torch.empty_like(q)
+        dkv32 = K.mha_bwd(q, kv[:, :Hd], kv[:, Hd:], o, do, lse, dq, s["P"], s["H"], s["hd"], s["Nq"], s["max_nk"],
+                          s["scale"], kv_row0=s["kv_row0"], kv_len=s["kv_len"])
+        if kv.dtype == torch.float32:
+            dkv = dkv32
+        else:
+            dkv = torch.empty_like(kv)
+            K.cast2d(dkv32, dkv)
+        return dq, dkv, None
+
+
+class BertEmbedFn(Function):
+    @staticmethod
+    def forward(ctx, anchor, tokens, emb, dtype):
+        ctx.tokens, ctx.emb = tokens, emb
+        return K.bert_embed_fwd(tokens, emb["word"].data, emb["pos"].data, emb["type"].data[0], dtype)
+
+    @staticmethod
+    def backward(ctx, de):
+        e = ctx.emb
+        K.bert_embed_bwd(de, ctx.tokens, e["word"].main_grad, e["pos"].main_grad, e["type"].main_grad[0])
+        return None, None, None, None
+
+
+class AstAssembleFn(Function):
+    @staticmethod
+    def forward(ctx, tok, cls, pos, BA, Pn):
+        ctx.cls, ctx.pos, ctx.BA, ctx.Pn = cls, pos, BA, Pn
+        return K.ast_assemble_fwd(tok.contiguous(), cls.data.view(-1), pos.data, BA, Pn)
+
+    @staticmethod
+    def backward(ctx, dx):
+        return K.ast_assemble_bwd(dx, ctx.cls.main_grad.view(-1), ctx.pos.main_grad, ctx.BA, ctx.Pn), None, None, None, None
+
+
+class MediaInputFn(Function):
+    """get_multimodal_forward_input_video/audio (modeling.py:485-502) writing the per-sample
+    cross-attention source [B, Sv+Sa, Hd] (video rows first, audio rows after: bert.py:450)."""
+
+    @staticmethod
+    def forward(ctx, vx, ax, pv, pa, B):
+        # vx: [B*nf*X, Hd] or None ; pv = (frame_emb param, type_emb param, nf, X)
+        parts = [(vx, pv), (ax, pa)]
+        S_total = sum(p[2] * p[3] for x, p in parts if x is not None)
+        ref = vx if vx is not None else ax
+        out = torch.empty(B * S_total, ref.shape[-1], device=ref.device, dtype=ref.dtype)
+        row0 = 0
+        rows = []
+        for x, p in parts:
+            if x is None:
+                rows.append(None)
+                continue
+            K.media_input_fwd(x.contiguous(), p[0].data.view(-1, ref.shape[-1]), p[1].data.view(-1), out, B, p[2], p[3],
+                              S_total, row0)
+            rows.append(row0)
+            row0 += p[2] * p[3]
+        ctx.parts, ctx.rows, ctx.B, ctx.S_total = (pv, pa), rows, B, S_total
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        grads = []
+        for p, row0 in zip(ctx.parts, ctx.rows):
+            if row0 is None:
+                grads.append(None)
+                continue
+            Hd = dout.shape[-1]
+            grads.append(K.media_input_bwd(dout, p[0].main_grad.view(-1, Hd), p[1].main_grad.view(-1), ctx.B, p[2], p[3],
+                                           ctx.S_total, row0))
+        return grads[0], grads[1], None, None, None
+
+
+class PatchMergeFn(Function):
+    @staticmethod
+    def forward(ctx, x, BD, H, W, C):
+        ctx.dims = (BD, H, W, C)
+        return K.patch_merge(x, BD, H, W, C, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.patch_merge(dy, *ctx.dims, True), None, None, None, None
+
+
+class MeanPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, R, X):
+        ctx.dims = (R, X)
+        return K.mean_pool_fwd(x, R, X)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.mean_pool_bwd(dy, *ctx.dims), None, None
+
+
+class SelectFirstFn(Function):
+    """x [R, X, C] -> x[:, 0, :]  (cls token per clip, modeling.py:399)."""
+
+    @staticmethod
+    def forward(ctx, x, R, X):
+        C = x.shape[-1]
+        x = x.contiguous()
+        y = torch.empty(R, C, device=x.device, dtype=x.dtype)
+        K.strided_rows(x.view(R, X * C)[:, :C], y)
+        ctx.dims = (R, X, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        R, X, C = ctx.dims
+        dx = torch.zeros(R * X, C, device=dy.device, dtype=dy.dtype)
+        K.strided_rows(dy.contiguous(), dx.view(R, X * C)[:, :C])
+        return dx, None, None
+
+
+class L2NormFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y, nrm = K.l2norm_fwd(x)
+        ctx.save_for_backward(x, nrm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, nrm = ctx.saved_tensors
+        return K.l2norm_bwd(dy, x, nrm)
+
+
+class FineSimFn(Function):
+    """compute_fine_matrix for the three modality groups at once (pretrain.py:178-211,302-345).
+    feat_t [Na*T, D], feat_va [Nb*Vt, D] (per sample: video slots then audio slots),
+    w_t [Na,T], w_v [Nb,nV], w_a [Nb,nA] raw fine weights (fp32), maskA [Na,T] uint8.
+    Returns scores [G, Na, Nb] for groups tva / tv / ta (those requested)."""
+
+    @staticmethod
+    def forward(ctx, feat_t, feat_va, w_t, w_v, w_a, maskA, dims, groups):
+        Na, Nb, T, nV, nA = dims
+        Vt = nV + nA
+        L = K.gemm(feat_t.contiguous(), feat_va.contiguous(), out_dtype=torch.float32)  # [Na*T, Nb*Vt]
+        wsA = K.masked_softmax_fwd(w_t, maskA)
+        scores, saved = [], []
+        for g in groups:
+            v0, nv = {"tva": (0, Vt), "tv": (0, nV), "ta": (nV, nA)}[g]
+            wB = {"tva": torch.cat((w_v, w_a), dim=1), "tv": w_v, "ta": w_a}[g].contiguous()
+            wsB = K.masked_softmax_fwd(wB, None)
+            sc, av, at = K.fine_reduce_fwd(L, maskA, wsA, wsB, Na, Nb, T, Vt, v0, nv)
+            scores.append(sc)
+            saved += [wsB, av, at]
+        ctx.save_for_backward(feat_t, feat_va, L, wsA, maskA, *saved)
+        ctx.dims, ctx.groups = dims, groups
+        return torch.stack(scores, 0)
+
+    @staticmethod
+    def backward(ctx, dscores):
+        feat_t, feat_va, L, wsA, maskA, *saved = ctx.saved_tensors
+        Na, Nb, T, nV, nA = ctx.dims
+        Vt = nV + nA
+        dL = torch.zeros_like(L)
+        dwsA = torch.zeros_like(wsA)
+        dw_v = torch.zeros(Nb, nV, device=L.device, dtype=torch.float32)
+        dw_a = torch.zeros(Nb, nA, device=L.device, dtype=torch.float32)
+        for i, g in enumerate(ctx.groups):
+            v0, nv = {"tva": (0, Vt), "tv": (0, nV), "ta": (nV, nA)}[g]
+            wsB, av, at = saved[3 * i: 3 * i + 3]
+            dwsB = torch.zeros_like(wsB)
+            K.fine_reduce_bwd(L, maskA, wsA, wsB, dscores[i], av, at, dL, dwsA, dwsB, Na, Nb, T, Vt, v0, nv)
+            dwB = K.masked_softmax_bwd(wsB, dwsB)
+            if g == "tva":
+                dw_v += dwB[:, :nV]
+                dw_a += dwB[:, nV:]
+            elif g == "tv":
+                dw_v += dwB
+            else:
+                dw_a += dwB
+        dw_t = K.masked_softmax_bwd(wsA, dwsA)
+        if feat_t.dtype != torch.float32:
+            dLl = torch.empty(dL.shape, device=dL.device, dtype=feat_t.dtype)
+            K.cast2d(dL, dLl)
+        else:
+            dLl = dL
+        dft = K.gemm(dLl, feat_va, b_kmajor=False)
+        dfva = K.gemm(dLl, feat_t, a_kmajor=False, b_kmajor=False)
+        return dft, dfva, dw_t, dw_v, dw_a, None, None, None
+
+
+class ContrastiveFn(Function):
+    """VALORModel.contrastive_loss (modeling.py:418-433) with the learnable temperature."""
+
+    @staticmethod
+    def forward(ctx, S, temp):
+        S = S.contiguous()
+        loss, rl, cl = K.contrastive_fwd(S, temp.data.view(1))
+        ctx.save_for_backward(S, rl, cl)
+        ctx.temp = temp
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        S, rl, cl = ctx.saved_tensors
+        g = g.contiguous().view(1).float()
+        return K.contrastive_bwd(S, ctx.temp.data.view(1), rl, cl, g, ctx.temp.main_grad.view(1)), None
+
+
+class XentFn(Function):
+    """F.cross_entropy(scores, labels) with labels == -1 ignored (pretrain.py:441-444)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, lse, acc = K.xent_fwd(logits, labels)
+        ctx.save_for_backward(logits, labels, lse, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse, acc = ctx.saved_tensors
+        g = g.contiguous().view(1).float()
+        return K.xent_bwd(logits, labels, lse, acc, g), None

@@ -1,0 +1,364 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point of
+include/valor_b200.h).  PyTorch is plumbing here: it owns device memory and the stream;
+all arithmetic happens inside libvalor_b200.so.  CPU tensors are rejected — there is no
+fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3
+BACKEND_AUTO, BACKEND_TENSOR, BACKEND_SIMT = 0, 1, 2
+
+launch_count = 0  # kernels-launched-through-the-ABI counter (bench.py's gpu_launches)
+
+
+def DT(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def P(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("valor_b200 kernels need CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ST():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    _lib.call(name, *args)
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, f"need a row-major 2-D view, got {tuple(t.shape)} {t.stride()}"
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------
+def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residual=None, act_aux=None,
+         want_preact=False, out=None, out_dtype=None, accumulate=False, alpha=1.0, backend=BACKEND_AUTO,
+         force_bn=0, force_splits=0):
+    """C[M,N] (+)= epi(alpha * A . B^T); a: [M,K] (k-major) or [K,M]; b: [N,K] (k-major) or [K,N]."""
+    M, K = (a.shape if a_kmajor else (a.shape[1], a.shape[0]))
+    N, Kb = (b.shape if b_kmajor else (b.shape[1], b.shape[0]))
+    assert K == Kb, f"gemm: contraction mismatch {K} vs {Kb}"
+    assert a.dtype == b.dtype
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype or a.dtype)
+    assert out.shape == (M, N)
+    preact = torch.empty(M, N, device=a.device, dtype=out.dtype) if want_preact else None
+    ep = _lib.ValorGemmEpilogue()
+    ep.bias = bias.data_ptr() if bias is not None else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    ep.residual = residual.data_ptr() if residual is not None else None
+    ep.ldr = _ld(residual) if residual is not None else 0
+    ep.res_dtype = DT(residual) if residual is not None else 0
+    ep.act_aux = act_aux.data_ptr() if act_aux is not None else None
+    ep.ld_aux = _ld(act_aux) if act_aux is not None else 0
+    ep.aux_dtype = DT(act_aux) if act_aux is not None else 0
+    ep.preact_out = preact.data_ptr() if preact is not None else None
+    ep.ld_pre = _ld(preact) if preact is not None else 0
+    ep.act = act
+    ep.out_dtype = DT(out)
+    ep.accumulate = 1 if accumulate else 0
+    ep.alpha = alpha
+    _call("valor_gemm", DT(a), P(a), _ld(a), int(a_kmajor), P(b), _ld(b), int(b_kmajor), P(out), _ld(out), M, N, K,
+          ctypes.byref(ep), backend, force_bn, force_splits, ST())
+    return (out, preact) if want_preact else out
+
+
+# ------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps):
+    M, N = x.shape
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    _call("valor_layernorm_fwd", DT(x), P(x), P(gamma), P(beta), P(y), P(mean), P(rstd), M, N, float(eps), ST())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
+    M, N = x.shape
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    _call("valor_layernorm_bwd", DT(x), P(dy), P(x), P(gamma), P(mean), P(rstd), P(dx), P(dgamma), P(dbeta), M, N, ST())
+    return dx
+
+
+def l2norm_fwd(x):
+    M, N = x.shape
+    y = torch.empty_like(x)
+    nrm = torch.empty(M, device=x.device, dtype=torch.float32)
+    _call("valor_l2norm_fwd", DT(x), P(x), P(y), P(nrm), M, N, ST())
+    return y, nrm
+
+
+def l2norm_bwd(dy, x, nrm):
+    M, N = x.shape
+    dx = torch.empty_like(x)
+    _call("valor_l2norm_bwd", DT(x), P(dy.contiguous()), P(x), P(nrm), P(dx), M, N, ST())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None, key_valid=None,
+            causal=None, backend=BACKEND_AUTO):
+    """q: [rows_q, >=H*hd] view, k/v: [rows_kv, >=H*hd] views (may alias one fused buffer)."""
+    o = torch.empty(q.shape[0], H * hd, device=q.device, dtype=q.dtype)
+    lse = torch.empty(P_, H, Nq, device=q.device, dtype=torch.float32)
+    _call("valor_mha_fwd", DT(q), P(q), P(k), P(v), _ld(q), _ld(k), _ld(v), P(o), _ld(o), P(lse), P_, H, hd, Nq,
+          max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal), float(scale), backend, ST())
+    return o, lse
+
+
+def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
+            key_valid=None, causal=None, backend=BACKEND_AUTO):
+    """dq_out: [rows_q, >=H*hd] view receiving dQ; returns fp32 (dK, dV) [rows_kv, H*hd] (accumulated)."""
+    dkv = torch.zeros(k.shape[0], 2 * H * hd, device=q.device, dtype=torch.float32)
+    dk, dv = dkv[:, : H * hd], dkv[:, H * hd:]
+    do = do.contiguous()
+    _call("valor_mha_bwd", DT(q), P(q), P(k), P(v), P(o), P(do), _ld(q), _ld(k), _ld(v), _ld(o), P(lse), P(dq_out),
+          _ld(dq_out), P(dk), P(dv), _ld(dk), _ld(dv), P_, H, hd, Nq, max_nk, P(q_row0), P(kv_row0), P(kv_len),
+          P(key_valid), P(causal), float(scale), backend, ST())
+    return dkv
+
+
+def window_attn_fwd(qkv, table, grid, win, shift, cfg_win, heads, hd, scale, backend=BACKEND_AUTO):
+    B, D, H, W = grid
+    o = torch.empty(qkv.shape[0], heads * hd, device=qkv.device, dtype=qkv.dtype)
+    nwin = B * (D // win[0]) * (H // win[1]) * (W // win[2])
+    lse = torch.empty(nwin, heads, win[0] * win[1] * win[2], device=qkv.device, dtype=torch.float32)
+    _call("valor_window_attn_fwd", DT(qkv), P(qkv), _ld(qkv), P(o), _ld(o), P(lse), P(table), B, D, H, W, *win, *shift,
+          *cfg_win, heads, hd, float(scale), backend, ST())
+    return o, lse
+
+
+def window_attn_bwd(qkv, o, do, lse, table, dtable, grid, win, shift, cfg_win, heads, hd, scale,
+                    backend=BACKEND_AUTO):
+    """returns dqkv [tokens, 3C] in qkv.dtype; dtable (fp32) accumulated in place."""
+    B, D, H, W = grid
+    C = heads * hd
+    dqkv = torch.empty_like(qkv)
+    dkv = torch.zeros(qkv.shape[0], 2 * C, device=qkv.device, dtype=torch.float32)
+    do = do.contiguous()
+    _call("valor_window_attn_bwd", DT(qkv), P(qkv), _ld(qkv), P(o), P(do), _ld(o), P(lse), P(table), P(dqkv),
+          _ld(dqkv), P(dkv[:, :C]), P(dkv[:, C:]), _ld(dkv), P(dtable), B, D, H, W, *win, *shift, *cfg_win, heads, hd,
+          float(scale), backend, ST())
+    cast2d(dkv, dqkv[:, C:])
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------
+# data movement
+# ------------------------------------------------------------------------------------------
+def swin_im2col(video, dtype):
+    B, F, C3, Hh, Ww = video.shape
+    assert C3 == 3 and video.is_contiguous()
+    cols = torch.empty(B * F * (Hh // 4) * (Ww // 4), 96, device=video.device, dtype=dtype)
+    _call("valor_swin_im2col", DT(video), DT(cols), P(video), P(cols), B, F, Hh, Ww, ST())
+    return cols
+
+
+def audio_im2col(spec, ps, dtype):
+    BA, mel, frames = spec.shape
+    assert spec.is_contiguous()
+    cols = torch.empty(BA * (mel // ps) * (frames // ps), ps * ps, device=spec.device, dtype=dtype)
+    _call("valor_audio_im2col", DT(spec), DT(cols), P(spec), P(cols), BA, mel, frames, ps, ST())
+    return cols
+
+
+def ast_assemble_fwd(tok, cls, pos, BA, Pn):
+    Hd = tok.shape[1]
+    x = torch.empty(BA * (Pn + 1), Hd, device=tok.device, dtype=tok.dtype)
+    _call("valor_ast_assemble_fwd", DT(tok), P(tok), P(cls), P(pos), P(x), BA, Pn, Hd, ST())
+    return x
+
+
+def ast_assemble_bwd(dx, dcls, dpos, BA, Pn):
+    Hd = dx.shape[1]
+    dx = dx.contiguous()
+    dtok = torch.empty(BA * Pn, Hd, device=dx.device, dtype=dx.dtype)
+    _call("valor_ast_assemble_bwd", DT(dx), P(dx), P(dtok), P(dcls), P(dpos), BA, Pn, Hd, ST())
+    return dtok
+
+
+def bert_embed_fwd(tokens, word, pos, type0, dtype):
+    R, Tn = tokens.shape
+    Hd = word.shape[1]
+    e = torch.empty(R * Tn, Hd, device=tokens.device, dtype=dtype)
+    _call("valor_bert_embed_fwd", DT(e), P(tokens), P(word), P(pos), P(type0), P(e), R, Tn, Hd, ST())
+    return e
+
+
+def bert_embed_bwd(de, tokens, dword, dpos, dtype0):
+    R, Tn = tokens.shape
+    Hd = de.shape[1]
+    de = de.contiguous()
+    _call("valor_bert_embed_bwd", DT(de), P(de), P(tokens), P(dword), P(dpos), P(dtype0), R, Tn, Hd, ST())
+
+
+def media_input_fwd(x, frame_emb, type_emb, out, B, nf, X, S_total, row0):
+    Hd = x.shape[-1]
+    _call("valor_media_input_fwd", DT(x), P(x), P(frame_emb), P(type_emb), P(out), B, nf, X, Hd, S_total, row0, ST())
+
+
+def media_input_bwd(dout, dframe, dtype_emb, B, nf, X, S_total, row0):
+    Hd = dout.shape[-1]
+    din = torch.empty(B * nf * X, Hd, device=dout.device, dtype=dout.dtype)
+    _call("valor_media_input_bwd", DT(dout), P(dout), P(din), P(dframe), P(dtype_emb), B, nf, X, Hd, S_total, row0, ST())
+    return din
+
+
+def patch_merge(src, BD, H, W, C, inverse):
+    src = src.contiguous()
+    if inverse:
+        dst = torch.empty(BD * H * W, C, device=src.device, dtype=src.dtype)
+    else:
+        dst = torch.empty(BD * (H // 2) * (W // 2), 4 * C, device=src.device, dtype=src.dtype)
+    _call("valor_patch_merge", DT(src), P(src), P(dst), BD, H, W, C, int(inverse), ST())
+    return dst
+
+
+def mean_pool_fwd(x, R, X):
+    C = x.shape[-1]
+    y = torch.empty(R, C, device=x.device, dtype=x.dtype)
+    _call("valor_mean_pool_fwd", DT(x), P(x.contiguous()), P(y), R, X, C, ST())
+    return y
+
+
+def mean_pool_bwd(dy, R, X):
+    C = dy.shape[-1]
+    dx = torch.empty(R * X, C, device=dy.device, dtype=dy.dtype)
+    _call("valor_mean_pool_bwd", DT(dy), P(dy.contiguous()), P(dx), R, X, C, ST())
+    return dx
+
+
+def colsum(dy, db):
+    M, N = dy.shape
+    _call("valor_colsum", DT(dy), P(dy), _ld(dy), P(db), M, N, ST())
+
+
+def cast2d(src, dst):
+    """dst[...] = cast(src[...]) for 2-D row-major (possibly strided) views of equal shape."""
+    assert src.shape == dst.shape
+    R, C = src.shape
+    _call("valor_cast2d", DT(src), DT(dst), P(src), _ld(src), P(dst), _ld(dst), R, C, ST())
+
+
+def cast_flat(src, dst):
+    n = src.numel()
+    assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous()
+    _call("valor_cast2d", DT(src), DT(dst), P(src), n, P(dst), n, 1, n, ST())
+
+
+def act_bwd(dy, h, act):
+    dy = dy.contiguous()
+    dh = torch.empty_like(h)
+    _call("valor_act_bwd", DT(h), P(dy), P(h), P(dh), h.numel(), act, ST())
+    return dh
+
+
+def strided_rows(src, dst, accumulate=False):
+    R, C = src.shape
+    assert dst.shape == src.shape
+    _call("valor_strided_rows", DT(src), P(src), _ld(src), P(dst), _ld(dst), R, C, int(accumulate), ST())
+
+
+# ------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------
+def xent_fwd(logits, labels):
+    M, V = logits.shape
+    lse = torch.empty(M, device=logits.device, dtype=torch.float32)
+    acc = torch.empty(2, device=logits.device, dtype=torch.float32)
+    loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+    _call("valor_xent_fwd", DT(logits), P(logits), _ld(logits), P(labels), P(lse), P(acc), P(loss), M, V, ST())
+    return loss, lse, acc
+
+
+def xent_bwd(logits, labels, lse, acc, g, gmul=1.0):
+    """in place: logits <- d loss / d logits * g"""
+    M, V = logits.shape
+    _call("valor_xent_bwd", DT(logits), P(logits), _ld(logits), P(labels), P(lse), P(acc), P(g), float(gmul),
+          P(logits), _ld(logits), M, V, ST())
+    return logits
+
+
+def masked_softmax_fwd(w, mask):
+    R, L = w.shape
+    ws = torch.empty_like(w)
+    _call("valor_masked_softmax_fwd", P(w.contiguous()), P(mask), P(ws), R, L, ST())
+    return ws
+
+
+def masked_softmax_bwd(ws, dws):
+    R, L = ws.shape
+    dw = torch.empty_like(ws)
+    _call("valor_masked_softmax_bwd", P(ws), P(dws.contiguous()), P(dw), R, L, ST())
+    return dw
+
+
+def fine_reduce_fwd(L, mA, wsA, wsB, Na, Nb, T, Vt, v0, nv):
+    score = torch.empty(Na, Nb, device=L.device, dtype=torch.float32)
+    arg_v = torch.empty(Na, Nb, T, device=L.device, dtype=torch.uint8)
+    arg_t = torch.empty(Na, Nb, nv, device=L.device, dtype=torch.uint8)
+    _call("valor_fine_reduce_fwd", P(L), _ld(L), P(mA), P(wsA), P(wsB), P(score), P(arg_v), P(arg_t), Na, Nb, T, Vt,
+          v0, nv, ST())
+    return score, arg_v, arg_t
+
+
+def fine_reduce_bwd(L, mA, wsA, wsB, dscore, arg_v, arg_t, dL, dwsA, dwsB, Na, Nb, T, Vt, v0, nv):
+    _call("valor_fine_reduce_bwd", P(L), _ld(L), P(mA), P(wsA), P(wsB), P(dscore.contiguous()), P(arg_v), P(arg_t),
+          P(dL), P(dwsA), P(dwsB), Na, Nb, T, Vt, v0, nv, ST())
+
+
+def contrastive_fwd(S, temp):
+    N = S.shape[0]
+    row_lse = torch.empty(N, device=S.device, dtype=torch.float32)
+    col_lse = torch.empty(N, device=S.device, dtype=torch.float32)
+    loss = torch.empty(1, device=S.device, dtype=torch.float32)
+    _call("valor_contrastive_fwd", P(S), P(temp), P(row_lse), P(col_lse), P(loss), N, ST())
+    return loss, row_lse, col_lse
+
+
+def contrastive_bwd(S, temp, row_lse, col_lse, g, dtemp, gmul=1.0):
+    N = S.shape[0]
+    dS = torch.empty_like(S)
+    _call("valor_contrastive_bwd", P(S), P(temp), P(row_lse), P(col_lse), P(g), float(gmul), P(dS), P(dtemp), N, ST())
+    return dS
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------
+def grad_sumsq(g, out):
+    _call("valor_grad_sumsq", P(g), g.numel(), P(out), ST())
+
+
+def clip_coef(sumsq, max_norm, norm_out):
+    _call("valor_clip_coef", P(sumsq), float(max_norm), P(norm_out), ST())
+
+
+def adamw(p, g, m, v, p_lp, hyper, coef):
+    _call("valor_adamw", P(p), P(g), P(m), P(v), P(p_lp), p.numel(), P(hyper), P(coef), ST())

@@ -1,0 +1,128 @@
+"""VALOR pretraining model — mirror of `model/pretrain.py` (class VALOR :64-134, forward_pt
+:214-541, compute_fine_matrix :178-211).  `VALOR(opts)`, `VALOR.from_pretrained(opts, sd)` and
+`VALOR.forward(batch, task, compute_loss=True) -> dict` keep the reference's signatures; the state
+dict keeps the reference's keys.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from . import kernels as K
+from .distributed import ddp_allgather, ddp_allgather_with_grads
+from .functional import lin_of
+from .modeling import VALORModel, default_opts  # noqa: F401
+from .videoswin import _Linear
+
+
+class Contra_head(nn.Module):
+    """pretrain.py:33-38"""
+
+    def __init__(self, input_dim, contra_dim):
+        super().__init__()
+        self.linear = _Linear(input_dim, contra_dim, bias=False)
+
+
+class VALOR(VALORModel):
+    def __init__(self, opts):
+        super().__init__(opts)
+        config = opts
+        self.contra_type = config.contra_type
+        self.caption_type = config.caption_type
+        self.contra_loss_ratio = config.contra_loss_ratio
+        self.use_task_prompt = config.use_task_prompt
+        self.late_fusion = config.late_fusion
+        self.full_masker = config.full_masker
+        if self.contra_type != "fine" or self.caption_type != "unimlm" or self.use_task_prompt or self.late_fusion \
+                or self.full_masker:
+            raise NotImplementedError("only the shipped pretraining recipe (fine contrastive + unimlm caption, no "
+                                      "task prompt) is on the hot path")
+        contra_dim = config.contra_dim
+        self.contra_head_t = Contra_head(self.txt_dim, contra_dim)
+        self.contra_head_v = Contra_head(self.video_dim, contra_dim)
+        self.contra_head_a = Contra_head(self.audio_dim, contra_dim)
+        for nm in ("text", "video", "audio"):  # pretrain.py:103-112 (index 1 is the ReLU)
+            seq = nn.Sequential(_Linear(contra_dim, contra_dim), nn.Identity(), _Linear(contra_dim, 1))
+            setattr(self, f"{nm}_fine_weight", seq)
+        self.contra_temp = nn.Parameter(torch.tensor(0.07))
+        self.contra_dim = contra_dim
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, batch, task, compute_loss=True):
+        if task.startswith("pt"):
+            return self.forward_pt(batch, task, compute_loss=compute_loss)
+        raise NotImplementedError("ret/cap/qa heads are the next §8 rows (SURVEY.md §8f N1-N3)")
+
+    def _fine_weight(self, feat, name):
+        seq = getattr(self, f"{name}_fine_weight")
+        h = Fn.linear(feat, lin_of(seq[0].weight, seq[0].bias), act=K.ACT_RELU)
+        return Fn.linear(h, lin_of(seq[2].weight, seq[2].bias), out_dtype=torch.float32)  # [rows, 1] fp32
+
+    def forward_pt(self, batch, task, compute_loss=True):
+        """pretrain.py:214-541 for compute_loss=True."""
+        assert compute_loss, "evaluation dict path is not part of the training hot path"
+        contra_task, caption_task = [], []
+        for t in task.split("_"):
+            if "mlm" in t:
+                raise NotImplementedError("the shipped pretraining task string has no mlm objective")
+            elif "caption" in t:
+                caption_task = t.split("%")[1:]
+            elif "contra" in t:
+                contra_task = t.split("%")[1:]
+        txt_tokens = batch["txt_tokens"]["bert_tokens"]
+        video_pixels = batch.get("video_pixels")
+        audio_spectrograms = batch.get("audio_spectrograms")
+        loss_dict = {}
+        used = "".join(caption_task + contra_task)
+        video_output = self.forward_video_encoder(video_pixels) if "v" in used else None
+        audio_output = self.forward_audio_encoder(audio_spectrograms) if "a" in used else None
+        B, T = txt_tokens.shape
+        dt = self.compute_dtype
+
+        if contra_task:
+            txt_output = self.forward_txt_encoder(txt_tokens)                                   # [B,T,768]
+            feat_t = Fn.L2NormFn.apply(Fn.linear(txt_output.reshape(B * T, -1), lin_of(self.contra_head_t.linear.weight)))
+            feat_t = ddp_allgather_with_grads.apply(feat_t.view(B, T, -1))
+            tokens_g = ddp_allgather(txt_tokens)
+            Na = feat_t.shape[0]
+            nV = nA = 0
+            feat_v = feat_a = None
+            if "v" in "".join(contra_task):
+                _, nV, X, C = video_output.shape
+                pooled = Fn.MeanPoolFn.apply(video_output.reshape(-1, C), B * nV, X)        # modeling.py:389
+                feat_v = Fn.L2NormFn.apply(Fn.linear(pooled, lin_of(self.contra_head_v.linear.weight)))
+                feat_v = ddp_allgather_with_grads.apply(feat_v.view(B, nV, -1))
+            if "a" in "".join(contra_task):
+                _, nA, X, C = audio_output.shape
+                cls = Fn.SelectFirstFn.apply(audio_output.reshape(-1, C), B * nA, X)        # modeling.py:399
+                feat_a = Fn.L2NormFn.apply(Fn.linear(cls, lin_of(self.contra_head_a.linear.weight)))
+                feat_a = ddp_allgather_with_grads.apply(feat_a.view(B, nA, -1))
+            D = feat_t.shape[-1]
+            w_t = self._fine_weight(feat_t.reshape(Na * T, D), "text").view(Na, T)
+            dev = feat_t.device
+            w_v = self._fine_weight(feat_v.reshape(Na * nV, D), "video").view(Na, nV) if feat_v is not None else \
+                torch.zeros(Na, 0, device=dev)
+            w_a = self._fine_weight(feat_a.reshape(Na * nA, D), "audio").view(Na, nA) if feat_a is not None else \
+                torch.zeros(Na, 0, device=dev)
+            parts = [f for f in (feat_v, feat_a) if f is not None]
+            feat_va = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]                  # pretrain.py:324
+            maskA = (tokens_g != 0).to(torch.uint8).contiguous()                               # pretrain.py:304
+            groups = [g for g in ("tva", "tv", "ta") if g in contra_task]                      # order of pretrain.py:397
+            scores = Fn.FineSimFn.apply(feat_t.reshape(Na * T, D), feat_va.reshape(-1, D), w_t, w_v, w_a, maskA,
+                                        (Na, Na, T, nV, nA), groups)
+            lo = [Fn.ContrastiveFn.apply(scores[i], self.contra_temp) for i in range(len(groups))]
+            loss_dict["contra_loss"] = (sum(lo) / len(lo) * self.contra_loss_ratio).reshape(())
+
+        if caption_task:
+            media, Sv, Sa = self.media_tokens(video_output, audio_output)                       # modeling.py:485-502
+            txt_input, txt_labels = self.text_masker(txt_tokens, 0.6)                           # pretrain.py:428
+            names = [n for n in ("tva", "tv", "ta") if n in caption_task]
+            ranges = {"tva": (0, Sv + Sa), "tv": (0, Sv), "ta": (Sv, Sa)}
+            npass = len(names)
+            tok_all = txt_input.repeat(npass, 1)
+            h = self.multimodal_encoder.encode(tok_all, [True] * npass, media, [ranges[n] for n in names], B)
+            logits = self.cls(h)                                                                # every position;
+            # labels == -1 rows are ignored.  Every pass shares the same labels, so the mean over all
+            # npass*B*T rows equals the reference's mean of per-pass means (pretrain.py:473-479).
+            labels = txt_labels.reshape(-1).repeat(npass)
+            loss_dict["caption_loss"] = Fn.XentFn.apply(logits, labels).reshape(())
+        return loss_dict
