@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — VALOR-base pretraining step throughput (samples/s) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port on host cores)
+
+One "step" = one full pretraining step of `pt_contra%tva%tv%ta_caption%tva%tv%ta` on one synthetic
+batch: VideoSwin-B + AST + BERT fusion forward, backward, (N>1: contrastive all-gathers + gradient
+all-reduce), grad-norm clip and AdamW — BASELINE.json configs[1]: per-GPU batch 32, 8 frames 224^2,
+2 audio clips (10 s), 32 tokens, bf16.  Dropout / DropPath are OFF on both arms (parity mode, see
+DESIGN.md) — stated in `config`.
+
+`value`  : whole-job samples/s with the batch already resident in HBM.
+`e2e`    : the same step through the public API `VALOR.forward(batch, task)` with the batch in
+           pinned HOST memory: H2D of pixels/spectrograms/tokens and the D2H read of the loss are
+           inside the timed region.
+`roofline`: the dominant kernel is the tcgen05 GEMM (88% of the step's FLOPs are Linear layers):
+           achieved = sum of executed GEMM FLOPs / sum of GEMM kernel time, measured with CUDA
+           events around every GEMM launch in one extra instrumented step of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TASK = "pt_contra%tva%tv%ta_caption%tva%tv%ta"
+FLOPS_PER_SAMPLE = 1178.8e9  # fwd+bwd matmul FLOPs / sample at F8 A2 T32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="valor_b200", choices=["valor_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--clips", type=int, default=2)
+    ap.add_argument("--tokens", type=int, default=32)
+    ap.add_argument("--geom", default="base", choices=["base", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference itself is Python and does not travel)
+# --------------------------------------------------------------------------------------------
+def cpu_step_fn(geom, B, F, A, T):
+    import torch
+    from oracle import synth, valor_oracle as vo
+    sd = synth.make_state_dict(geom, seed=0, include_buffers=False)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if not k.startswith("txt_encoder.") and k != "cls.decoder.weight"}
+    full = dict(params)
+    for k in sd:
+        if k.startswith("txt_encoder."):
+            full[k] = params["multimodal_encoder." + k[len("txt_encoder."):]]
+    full["cls.decoder.weight"] = params["multimodal_encoder.embeddings.word_embeddings.weight"]
+    batch = synth.make_batch(B, F, A, T, geom, seed=123)
+    ti, tl = synth.token_masker(batch["txt_tokens"]["bert_tokens"], 0.6, seed=1234)
+    state = {k: (torch.zeros_like(p), torch.zeros_like(p)) for k, p in params.items()}
+    step = [0]
+
+    def run():
+        step[0] += 1
+        losses = vo.forward_pt(batch, full, geom, ti, tl, task=TASK)
+        for p in params.values():
+            p.grad = None
+        sum(losses.values()).backward()
+        grads = [p.grad for p in params.values() if p.grad is not None]
+        vo.clip_grad_norm_(grads, 5.0)
+        with torch.no_grad():
+            for k, p in params.items():
+                if p.grad is not None:
+                    vo.adamw_step(p, p.grad, state[k][0], state[k][1], step[0], 1e-4,
+                                  weight_decay=0.0 if vo.is_no_decay(k) else 0.01)
+        return {k: v.item() for k, v in losses.items()}
+
+    return run
+
+
+def cpu_baseline(geom, F, A, T, steps=2, warmup=1, B=2):
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    run = cpu_step_fn(geom, B, F, A, T)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        losses = run()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} full steps (fwd+bwd+clip+AdamW) of the oracle port at B={B} F={F} A={A} T={T} fp32, "
+                      f"{warmup} warm-up; {dt:.2f} s/step", "ms_per_step": dt * 1e3, "losses": losses}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+    geom = synth.BASE if args.geom == "base" else synth.TINY
+    cb = cpu_baseline(geom, args.frames, args.clips, args.tokens, steps=max(1, min(args.steps, 3)),
+                      warmup=max(1, min(args.warmup, 1)))
+    line = {"metric": "pretrain samples/sec (video+audio+text)", "value": cb["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": f"VALOR-base pretrain step (Swin-B+AST+BERT), oracle port of the reference on host "
+                                   f"CPU, B=2 F={args.frames} A={args.clips} T={args.tokens}", "task": TASK,
+                       "dropout": "off"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return main_reference(args)
+    import torch
+    import torch.distributed as dist
+    from oracle import synth  # seeded synthetic weights/batch only (not the checker)
+    from valor_b200 import kernels as K
+    from valor_b200.distributed import allreduce_grads
+    from valor_b200.optim import get_lr_sched
+    from valor_b200.pretrain import VALOR, default_opts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    geom = synth.BASE if args.geom == "base" else synth.TINY
+    B, F, A, T = args.batch, args.frames, args.clips, args.tokens
+    opts = default_opts(swin_depths=geom.swin_depths, ast_layers=geom.ast_layers, bert_layers=geom.bert_layers,
+                        num_train_steps=1000)
+    model = VALOR.from_pretrained(opts, synth.make_state_dict(geom, seed=0))
+    store = model.attach(dtype=torch.bfloat16, device=dev)
+    host = synth.make_batch(B, F, A, T, geom, seed=123 + rank)
+    tokens_h = host["txt_tokens"]["bert_tokens"]
+    mask_h = synth.token_masker(tokens_h, 0.6, seed=1234 + rank)   # host-side draw (TokenMasker is host code)
+    pinned = {"video": host["video_pixels"].pin_memory(), "audio": host["audio_spectrograms"].pin_memory(),
+              "tokens": tokens_h.pin_memory(), "mi": mask_h[0].pin_memory(), "ml": mask_h[1].pin_memory()}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values())
+
+    def to_device():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        return {"video_pixels": d["video"], "audio_spectrograms": d["audio"], "txt_tokens": {"bert_tokens": d["tokens"]},
+                "caption_mask": (d["mi"], d["ml"]), "ids": host["ids"]}
+
+    resident = to_device()
+    gstep = [0]
+
+    def train_step(batch):
+        gstep[0] += 1
+        store.zero_grad()
+        losses = model(batch, TASK, compute_loss=True)
+        sum(losses.values()).backward()
+        allreduce_grads(store)
+        store.set_hyper(get_lr_sched(gstep[0], opts), base_lr=opts.learning_rate, betas=tuple(opts.betas),
+                        weight_decay=opts.weight_decay)
+        store.optimizer_step(max_norm=opts.grad_norm)
+        return losses
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps, out
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = K.launch_count
+    ms_step, losses = timed(lambda: train_step(resident), args.steps)
+    launches = (K.launch_count - l0) // args.steps
+
+    def e2e_step():
+        losses = train_step(to_device())
+        return {k: v.item() for k, v in losses.items()}     # D2H read of the step's result
+
+    e2e_step()
+    ms_e2e, loss_vals = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline pass: CUDA events around every GEMM launch of one more step (outside the timed region)
+    roof = None
+    peak_tf, peak_hbm, peak_kind = peaks()
+    if not args.no_roofline and rank == 0:
+        recs = []
+        orig = K.gemm
+
+        def gemm_probe(a, b, **kw):
+            M, Kd = (a.shape if kw.get("a_kmajor", True) else (a.shape[1], a.shape[0]))
+            N = b.shape[0] if kw.get("b_kmajor", True) else b.shape[1]
+            tensor = a.dtype == torch.bfloat16 and N >= 8 and Kd >= 8 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(a, b, **kw)
+            e.record()
+            recs.append((2.0 * M * N * Kd, s, e, tensor))
+            return r
+
+        K.gemm = gemm_probe
+        try:
+            train_step(resident)
+            torch.cuda.synchronize()
+        finally:
+            K.gemm = orig
+        t_ms = sum(s.elapsed_time(e) for f, s, e, t in recs if t)
+        fl = sum(f for f, s, e, t in recs if t)
+        n_t = sum(1 for r in recs if r[3])
+        ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_kind": f"{peak_kind} (sustained bf16)",
+                "launches_per_step": n_t, "gemm_ms_per_step": t_ms, "gemm_tflop_per_step": fl / 1e12,
+                "gemm_share_of_step": t_ms / ms_step}
+
+    value = world * B / (ms_step * 1e-3)
+    e2e_val = world * B / (ms_e2e * 1e-3)
+    line = {"metric": "pretrain samples/sec (video+audio+text)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"VALOR-base (VideoSwin-B + AST + BERT-base fusion) pretrain step, per-GPU batch {B}, "
+                                   f"{F} frames 224^2, {A} audio clips, {T} tokens (BASELINE configs[1])",
+                       "task": TASK, "global_batch": world * B, "parallelism": f"dp{world}", "dropout": "off (parity mode)",
+                       "l2": "inputs larger than L2 (154 MB pixels/step), weights+activations >> 126 MB",
+                       "geom": args.geom},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4 * len(loss_vals)},
+            "gpu_launches": launches, "clocks": clocks, "losses": loss_vals,
+            "step_mfu": FLOPS_PER_SAMPLE * B / (ms_step * 1e-3) / (peak_tf * 1e12) if args.geom == "base" else None}
+    if roof:
+        line["roofline"] = roof
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(geom, F, A, T, steps=2, warmup=1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,7 +114,12 @@ class VALOR(VALORModel):
 
         if caption_task:
             media, Sv, Sa = self.media_tokens(video_output, audio_output)                       # modeling.py:485-502
-            txt_input, txt_labels = self.text_masker(txt_tokens, 0.6)                           # pretrain.py:428
+            if batch.get("caption_mask") is not None:
+                # the TokenMasker draw (host Python RNG in the reference, modeling.py:134-174) taken in
+                # the input pipeline from the host copy of the tokens: no device->host sync in the step
+                txt_input, txt_labels = batch["caption_mask"]
+            else:
+                txt_input, txt_labels = self.text_masker(txt_tokens, 0.6)                       # pretrain.py:428
             names = [n for n in ("tva", "tv", "ta") if n in caption_task]
             ranges = {"tva": (0, Sv + Sa), "tv": (0, Sv), "ta": (Sv, Sa)}
             npass = len(names)
