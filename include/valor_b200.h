@@ -101,16 +101,17 @@ int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const 
  * order.  qkv [B*D*H*W, 3*heads*hd] (q | k | v), O [B*D*H*W, heads*hd].  (wd,wh,ww)/(sd,sh,sw)
  * are the EFFECTIVE window / shift (get_window_size, videoswin.py:86-99); (WD,WH,WW) the
  * configured window that sizes `table` = relative_position_bias_table [(2WD-1)(2WH-1)(2WW-1), heads].
- * Backward: dqkv's q third is written, k/v thirds accumulate into fp32 dK/dV [tokens, heads*hd]
- * (caller zero-fills); dtable accumulates (+=). */
+ * Backward: dqkv [tokens, 3*heads*hd] receives dq | dk | dv; dtable accumulates (+=).  The SIMT
+ * path needs an fp32 scratch of valor_window_attn_bwd_scratch_bytes() bytes, zero-filled by the
+ * caller (the tensor-core path returns 0 and takes NULL). */
 int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, long long ldo, float* lse,
                           const float* table, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh,
                           int sw, int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream);
+long long valor_window_attn_bwd_scratch_bytes(int dtype, long long tokens, int heads, int hd, long long ld, int backend);
 int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
-                          const float* lse, const float* table, void* dQ, long long lddq, float* dK, float* dV,
-                          long long lddkv, float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd,
-                          int sh, int sw, int WD, int WH, int WW, int heads, int hd, float scale, int backend,
-                          void* stream);
+                          const float* lse, const float* table, void* dqkv, long long lddqkv, float* scratch,
+                          float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
+                          int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream);
 
 /* ---- data movement around the GEMMs --------------------------------------------------------- */
 /* PatchEmbed3D as GEMM (videoswin.py:361-369): video [B,F,3,Hh,Ww] -> cols [B*F*Hh/4*Ww/4, 96] */

@@ -31,7 +31,7 @@ def parse_header(path=HEADER):
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     text = re.sub(r"typedef struct .*?\} \w+;", " ", text, flags=re.S)
     decls = {}
-    for m in re.finditer(r"(const char\*|int)\s+(valor_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(const char\*|long long|int)\s+(valor_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -47,7 +47,8 @@ def parse_header(path=HEADER):
                     argtypes.append(ctypes.c_int)
                 else:
                     raise ValorLibraryError(f"cannot parse argument '{a}' of {name}")
-        decls[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+        restype = ctypes.c_char_p if ret.startswith("const char") else (ctypes.c_longlong if ret == "long long" else ctypes.c_int)
+        decls[name] = (restype, argtypes)
     return decls
 
 

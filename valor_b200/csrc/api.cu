@@ -59,6 +59,17 @@ int contrastive_bwd(const float*, const float*, const float*, const float*, cons
 int grad_sumsq(const float*, long long, float*, cudaStream_t);
 int clip_coef(const float*, float, float*, cudaStream_t);
 int adamw(float*, const float*, float*, float*, void*, long long, const float*, const float*, cudaStream_t);
+bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
+                       const void* k, const void* v, const void* o);
+int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
+                long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
+int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ, long long lddq,
+                float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
+int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
+                   int H, int hd, float scale, cudaStream_t st);
+int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
+                   const float* lse, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd, float scale, cudaStream_t st);
 
 }  // namespace valor
 
@@ -124,7 +135,9 @@ int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long l
                   float scale, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
-  (void)backend;
+  const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O);
+  if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_fwd: tensor backend requested but not eligible");
+  if (backend != VALOR_BACKEND_SIMT && ok) return mha_mma_fwd(ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, ST);
   return mha_ref_fwd(dtype, ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, ST);
 }
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
@@ -134,7 +147,11 @@ int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const 
                   const unsigned char* key_valid, const unsigned char* causal, float scale, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
-  (void)backend;
+  const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O) && (lddq % 8 == 0) &&
+                  (((uintptr_t)dQ | (uintptr_t)dO) & 15) == 0 && Nq <= 448;
+  if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_bwd: tensor backend requested but not eligible");
+  if (backend != VALOR_BACKEND_SIMT && ok)
+    return mha_mma_bwd(ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq, scale, ST);
   return mha_ref_bwd(dtype, ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq,
                      scale, ST);
 }
@@ -159,19 +176,37 @@ int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, lon
   WindowIndex ix;
   if (make_window(ix, table, B, D, H, W, wd, wh, ww, sd, sh, sw, WD, WH, WW, heads)) return 1;
   const int P = B * (D / wd) * (H / wh) * (W / ww);
-  (void)backend;
+  const char* qb = (const char*)qkv;
+  const bool ok = attn_mma_eligible(dtype, hd, ld, ld, ld, ldo, qb, qb + 2 * heads * hd, qb + 4 * heads * hd, O);
+  if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_window_attn_fwd: tensor backend requested but not eligible");
+  if (backend != VALOR_BACKEND_SIMT && ok) return window_mma_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
   return window_ref_fwd(dtype, ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
 }
+static bool window_bwd_tensor_ok(int dtype, int hd, long long ld, int backend) {
+  return backend != VALOR_BACKEND_SIMT && dtype == VALOR_DT_BF16 && (hd == 32 || hd == 64) && (ld % 8 == 0);
+}
+long long valor_window_attn_bwd_scratch_bytes(int dtype, long long tokens, int heads, int hd, long long ld, int backend) {
+  if (window_bwd_tensor_ok(dtype, hd, ld, backend)) return 0;
+  return tokens * 2LL * heads * hd * (long long)sizeof(float);
+}
 int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
-                          const float* lse, const float* table, void* dQ, long long lddq, float* dK, float* dV,
-                          long long lddkv, float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd,
-                          int sh, int sw, int WD, int WH, int WW, int heads, int hd, float scale, int backend,
-                          void* stream) {
+                          const float* lse, const float* table, void* dqkv, long long lddqkv, float* scratch,
+                          float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
+                          int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream) {
   WindowIndex ix;
   if (make_window(ix, table, B, D, H, W, wd, wh, ww, sd, sh, sw, WD, WH, WW, heads)) return 1;
   const int P = B * (D / wd) * (H / wh) * (W / ww);
-  (void)backend;
-  return window_ref_bwd(dtype, ix, qkv, ld, O, dO, ldo, lse, dQ, lddq, dK, dV, lddkv, dtable, P, heads, hd, scale, ST);
+  const int C = heads * hd;
+  const long long tokens = (long long)B * D * H * W;
+  if (window_bwd_tensor_ok(dtype, hd, ld, backend) && lddqkv % 8 == 0 && ldo % 8 == 0 &&
+      ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) && ix.N <= 448)
+    return window_mma_bwd(ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);
+  VALOR_REQUIRE(scratch != nullptr, "valor_window_attn_bwd: SIMT path needs the fp32 scratch buffer");
+  if (window_ref_bwd(dtype, ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, scratch, scratch + C, 2 * C, dtable, P, heads,
+                     hd, scale, ST))
+    return 1;
+  const size_t es = dtype == VALOR_DT_F32 ? 4 : 2;
+  return cast2d(VALOR_DT_F32, dtype, scratch, 2 * C, (char*)dqkv + C * es, lddqkv, tokens, 2 * C, ST);
 }
 
 int valor_swin_im2col(int in_dtype, int dtype, const void* video, void* cols, int B, int F, int Hh, int Ww, void* stream) {

@@ -1,0 +1,574 @@
+// valor_b200 — tensor-core flash attention (bf16, fp32 accumulate / softmax) for the three
+// attention shapes of the step: VideoSwin shifted-window attention (N<=392 keys, hd 32),
+// BERT/AST self attention (32..129 tokens, hd 64) and BERT cross attention (32 queries x
+// 258..650 media keys, hd 64).  S and P never leave the SM: scores live in mma accumulators,
+// the backward recomputes them from the saved log-sum-exp (the reference materialises the full
+// softmax map for autograd: ~19.5 GB per step over the 24 Swin blocks).
+//
+// Window case: cyclic shift, window partition, relative-position bias and the -100 shift mask
+// are evaluated from three small per-window tables built in shared memory at CTA start
+// (row index, relative-position code, mask region) — nothing is gathered or rolled in HBM.
+//
+// MMA path: mma.sync.m16n8k16 (bf16) with ldmatrix operand fetch.  The softmax/bias/mask
+// element work, not the MMA issue rate, bounds these kernels at hd 32.
+#include "common.cuh"
+#include "attention.cuh"
+
+namespace valor {
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+
+static constexpr int BQ = 64, BKEY = 64;
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+// ---- per-problem tables in shared memory -------------------------------------------------
+struct Tables {
+  int* qrow;            // [NqPad] global row of query i (-1 = padding)
+  int* krow;            // [NkPad]
+  short* code;          // window: relative-position code per local token
+  unsigned char* reg;   // window: mask region per local token
+  unsigned char* kval;  // mha: key validity
+  float* tab;           // window: this head's column of the bias table
+  int center, causal, nq, nk;
+};
+
+template <bool WINDOW>
+__device__ __forceinline__ float add_term(const Tables& t, int i, int j) {
+  if (WINDOW) {
+    float a = t.tab[t.code[i] - t.code[j] + t.center];
+    if (t.reg[i] != t.reg[j]) a += -100.0f;
+    return a;
+  } else {
+    const bool masked = (t.kval != nullptr && t.kval[j] == 0) || (t.causal && j > i);
+    return masked ? -10000.0f : 0.0f;
+  }
+}
+
+struct AttnParams {
+  const bf16 *Q, *K, *V;
+  long long ldq, ldk, ldv;
+  bf16* O;  // fwd out / bwd: saved O
+  long long ldo;
+  float* lse;
+  int H, hd, Nq, max_nk;
+  float scale;
+  // backward
+  const bf16* dO;
+  bf16* dQ; long long lddq;
+  bf16* dK_lp; bf16* dV_lp; long long lddkv_lp;      // direct bf16 outputs (window / self)
+  float* dK; float* dV; long long lddk, lddv;         // fp32 accumulate outputs (cross: shared K/V rows)
+  float* dtable;
+  MhaIndex mha;
+  WindowIndex win;
+};
+
+template <bool WINDOW>
+__device__ void build_tables(Tables& t, unsigned char* base, const AttnParams& P, int p, int h, int nq_pad, int nk_pad) {
+  // carve
+  t.qrow = (int*)base; base += sizeof(int) * nq_pad;
+  if (WINDOW) {
+    t.krow = t.qrow;
+    t.code = (short*)base; base += sizeof(short) * nq_pad;
+    t.reg = base; base += (nq_pad + 15) / 16 * 16;
+    t.kval = nullptr;
+    t.tab = (float*)base;
+    const WindowIndex& ix = P.win;
+    t.nq = t.nk = ix.N;
+    t.causal = 0;
+    const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
+    t.center = (ix.WD - 1) * cH + (ix.WH - 1) * cW + (ix.WW - 1);
+    for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {
+      if (i < ix.N) {
+        int cd, ch, cw, b;
+        ix.coords(p, i, cd, ch, cw, b);
+        t.qrow[i] = (int)ix.row(p, i);
+        const int ld = i / (ix.wh * ix.ww), lh = (i / ix.ww) % ix.wh, lw = i % ix.ww;
+        t.code[i] = (short)(ld * cH + lh * cW + lw);
+        t.reg[i] = (unsigned char)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
+                                   ix.region(cw, ix.W, ix.ww, ix.sw));
+      } else {
+        t.qrow[i] = -1; t.code[i] = 0; t.reg[i] = 0;
+      }
+    }
+    const int n_rel = (2 * ix.WD - 1) * cH;
+    for (int r = threadIdx.x; r < n_rel; r += blockDim.x) t.tab[r] = ix.table[(size_t)r * ix.heads + h];
+  } else {
+    t.krow = (int*)base; base += sizeof(int) * nk_pad;
+    t.kval = base;
+    t.code = nullptr; t.reg = nullptr; t.tab = nullptr; t.center = 0;
+    const MhaIndex& ix = P.mha;
+    t.nq = ix.Nq;
+    t.nk = ix.nk(p);
+    t.causal = ix.causal ? (int)ix.causal[p] : 0;
+    for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) t.qrow[i] = i < t.nq ? (int)ix.qrow(p, i) : -1;
+    for (int j = threadIdx.x; j < nk_pad; j += blockDim.x) {
+      t.krow[j] = j < t.nk ? (int)ix.krow(p, j) : -1;
+      t.kval[j] = (j < t.nk && (ix.key_valid == nullptr || ix.key_valid[(size_t)p * ix.max_nk + j])) ? 1 : 0;
+    }
+    if (ix.key_valid == nullptr) t.kval = t.kval;  // all ones within nk; padding handled by nk bound
+  }
+}
+
+// gather 64 rows x HD bf16 (16-byte chunks) into a padded smem tile; rows < 0 -> zeros
+template <int HD>
+__device__ __forceinline__ void load_tile(unsigned char* dst, const bf16* src, long long ld, int col0, const int* rows, int r0) {
+  constexpr int PITCH = HD * 2 + 16, CH = HD / 8;
+  for (int c = threadIdx.x; c < 64 * CH; c += blockDim.x) {
+    const int r = c / CH, ch = c % CH;
+    const int gr = rows[r0 + r];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gr >= 0) v = *(const uint4*)(src + (size_t)gr * ld + col0 + ch * 8);
+    *(uint4*)(dst + r * PITCH + ch * 16) = v;
+  }
+}
+
+// ==========================================================================================
+// forward: grid (ceil(Nq/64), P, H), 128 threads; warp w owns query rows [w*16, w*16+16)
+// ==========================================================================================
+template <int HD, bool WINDOW>
+__global__ void __launch_bounds__(128)
+attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
+  constexpr int PITCH = HD * 2 + 16;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* Qs = smem;
+  unsigned char* Ks = Qs + 64 * PITCH;
+  unsigned char* Vs = Ks + 64 * PITCH;
+  __shared__ Tables T;
+  const int p = blockIdx.y, h = blockIdx.z, qb = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  Tables t;
+  build_tables<WINDOW>(t, Vs + 64 * PITCH, P, p, h, nq_pad, nk_pad);
+  __syncthreads();
+  const int col0 = h * HD;
+  load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
+  __syncthreads();
+  uint32_t qf[HD / 16][4];
+  {
+    const int m = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks)
+      ldsm_x4(qf[ks], s_u32(Qs + (warp * 16 + (m & 1) * 8 + r) * PITCH + (ks * 16 + (m >> 1) * 8) * 2));
+  }
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const int i0 = qb * BQ + warp * 16 + g;  // rows i0 and i0+8
+  const float sc2 = P.scale * LOG2E;
+  const int nkb = (t.nk + BKEY - 1) / BKEY;
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
+    load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    {
+      const int m = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt += 2) {
+          uint32_t b[4];
+          ldsm_x4(b, s_u32(Ks + ((nt + (m >> 1)) * 8 + r) * PITCH + (ks * 16 + (m & 1) * 8) * 2));
+          mma16816(s[nt], qf[ks], b);
+          mma16816(s[nt + 1], qf[ks], b + 2);
+        }
+    }
+    // scale + bias/mask (log2 domain), running max
+    float mnew[2] = {mrow[0], mrow[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + (e >> 1) * 8, j = kb * BKEY + nt * 8 + t4 * 2 + (e & 1);
+        float v = -INFINITY;
+        if (j < t.nk && i < t.nq) v = s[nt][e] * sc2 + add_term<WINDOW>(t, i, j) * LOG2E;
+        s[nt][e] = v;
+        mnew[e >> 1] = fmaxf(mnew[e >> 1], v);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
+      mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
+    }
+    float corr[2], msafe[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      msafe[r] = mnew[r] == -INFINITY ? 0.f : mnew[r];
+      corr[r] = exp2f(mrow[r] - msafe[r]);  // mrow=-inf -> 0
+      mrow[r] = mnew[r];
+      lrow[r] *= corr[r];
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(s[nt][e] - msafe[e >> 1]);
+        s[nt][e] = pv;
+        lrow[e >> 1] += pv;
+      }
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(s[nt][0], s[nt][1]);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(s[nt][2], s[nt][3]);
+    }
+    {
+      const int m = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; dt += 2) {
+          uint32_t b[4];
+          ldsm_x4_t(b, s_u32(Vs + (kk * 16 + (m & 1) * 8 + r) * PITCH + ((dt + (m >> 1)) * 8) * 2));
+          mma16816(o[dt], pf[kk], b);
+          mma16816(o[dt + 1], pf[kk], b + 2);
+        }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + r * 8;
+    if (i < t.nq) {
+      const float inv = 1.f / lrow[r];
+      bf16* dst = P.O + (size_t)t.qrow[i] * P.ldo + col0;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt)
+        *(uint32_t*)(dst + dt * 8 + t4 * 2) = pack_bf16(o[dt][r * 2] * inv, o[dt][r * 2 + 1] * inv);
+      if (t4 == 0) P.lse[((size_t)p * P.H + h) * P.Nq + i] = mrow[r] * LN2 + __logf(lrow[r]);
+    }
+  }
+}
+
+// ==========================================================================================
+// backward: one CTA per (problem, head); 128 threads.
+//   outer loop: key blocks (dK/dV of 16 keys per warp live in registers)
+//   inner loop: query blocks; phase 1 warps own queries (S, P, dP, dS, dQ), phase 2 warps own
+//   keys (dV += P^T dO, dK += dS^T Q) after P / dS went through shared memory.
+//   dQ accumulates in a shared-memory fp32 panel (rows owned by one warp at a time).
+// ==========================================================================================
+template <int HD, bool WINDOW>
+__global__ void __launch_bounds__(128)
+attn_mma_bwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
+  constexpr int PITCH = HD * 2 + 16, PP = 64 * 2 + 16;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* Qs = smem;
+  unsigned char* dOs = Qs + 64 * PITCH;
+  unsigned char* Ks = dOs + 64 * PITCH;
+  unsigned char* Vs = Ks + 64 * PITCH;
+  unsigned char* Ps = Vs + 64 * PITCH;
+  unsigned char* dSs = Ps + 64 * PP;
+  float* dQacc = (float*)(dSs + 64 * PP);       // [nq_pad][HD]
+  float* lse_s = dQacc + (size_t)nq_pad * HD;    // [nq_pad]
+  float* del_s = lse_s + nq_pad;                 // [nq_pad]
+  float* dtab_s = del_s + nq_pad;                // window: [n_rel]
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  int n_rel = 0;
+  if (WINDOW) n_rel = (2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
+  Tables t;
+  build_tables<WINDOW>(t, (unsigned char*)(dtab_s + n_rel), P, p, h, nq_pad, nk_pad);
+  for (int i = threadIdx.x; i < nq_pad * HD; i += blockDim.x) dQacc[i] = 0.f;
+  for (int i = threadIdx.x; i < n_rel; i += blockDim.x) dtab_s[i] = 0.f;
+  __syncthreads();
+  const int col0 = h * HD;
+  // lse and delta = rowsum(dO * O) per query
+  for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {
+    float l = 0.f, d = 0.f;
+    if (i < t.nq) {
+      l = P.lse[((size_t)p * P.H + h) * P.Nq + i];
+      const bf16* orow = P.O + (size_t)t.qrow[i] * P.ldo + col0;
+      const bf16* drow = P.dO + (size_t)t.qrow[i] * P.ldo + col0;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        const uint4 a = *(const uint4*)(orow + c), b = *(const uint4*)(drow + c);
+        const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
+        const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+          d += fa.x * fb.x + fa.y * fb.y;
+        }
+      }
+    }
+    lse_s[i] = l;
+    del_s[i] = d;
+  }
+  const float sc = P.scale;
+  const int nkb = (t.nk + BKEY - 1) / BKEY, nqb = (t.nq + BQ - 1) / BQ;
+  const int m8 = lane >> 3, r8 = lane & 7;
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
+    load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
+    float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
+    for (int qb = 0; qb < nqb; ++qb) {
+      __syncthreads();
+      load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
+      load_tile<HD>(dOs, P.dO, P.ldo, col0, t.qrow, qb * BQ);
+      __syncthreads();
+      // ---------------- phase 1: warp owns queries [warp*16, +16) of this block ----------------
+      {
+        uint32_t qf[HD / 16][4], dof[HD / 16][4];
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          ldsm_x4(qf[ks], s_u32(Qs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+          ldsm_x4(dof[ks], s_u32(dOs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+        }
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < 8; nt += 2) {
+            uint32_t b[4];
+            ldsm_x4(b, s_u32(Ks + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+            mma16816(s[nt], qf[ks], b);
+            mma16816(s[nt + 1], qf[ks], b + 2);
+            ldsm_x4(b, s_u32(Vs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+            mma16816(dp[nt], dof[ks], b);
+            mma16816(dp[nt + 1], dof[ks], b + 2);
+          }
+        const int il = warp * 16 + g;            // local rows il, il+8 within the q block
+        const int i0 = qb * BQ + il;
+        uint32_t dsf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          float pv[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i0 + (e >> 1) * 8, j = kb * BKEY + nt * 8 + t4 * 2 + (e & 1);
+            float pr = 0.f, d = 0.f;
+            if (i < t.nq && j < t.nk) {
+              const float sv = s[nt][e] * sc + add_term<WINDOW>(t, i, j);
+              pr = __expf(sv - lse_s[i]);
+              d = pr * (dp[nt][e] - del_s[i]);
+              if (WINDOW) atomicAdd(&dtab_s[t.code[i] - t.code[j] + t.center], d);
+            }
+            pv[e] = pr;
+            ds[e] = d * sc;
+          }
+          // P and dS (bf16) to shared memory, [query][key]
+          *(uint32_t*)(Ps + il * PP + (nt * 8 + t4 * 2) * 2) = pack_bf16(pv[0], pv[1]);
+          *(uint32_t*)(Ps + (il + 8) * PP + (nt * 8 + t4 * 2) * 2) = pack_bf16(pv[2], pv[3]);
+          const uint32_t d01 = pack_bf16(ds[0], ds[1]), d23 = pack_bf16(ds[2], ds[3]);
+          *(uint32_t*)(dSs + il * PP + (nt * 8 + t4 * 2) * 2) = d01;
+          *(uint32_t*)(dSs + (il + 8) * PP + (nt * 8 + t4 * 2) * 2) = d23;
+          dsf[nt >> 1][(nt & 1) * 2 + 0] = d01;
+          dsf[nt >> 1][(nt & 1) * 2 + 1] = d23;
+        }
+        // dQ_w += dS_w . K_blk
+        float dq[HD / 8][4];
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int dt = 0; dt < HD / 8; dt += 2) {
+            uint32_t b[4];
+            ldsm_x4_t(b, s_u32(Ks + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+            mma16816(dq[dt], dsf[kk], b);
+            mma16816(dq[dt + 1], dsf[kk], b + 2);
+          }
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; ++dt) {
+          float* r0p = dQacc + (size_t)(i0)*HD + dt * 8 + t4 * 2;
+          float* r1p = dQacc + (size_t)(i0 + 8) * HD + dt * 8 + t4 * 2;
+          if (i0 < nq_pad) { r0p[0] += dq[dt][0]; r0p[1] += dq[dt][1]; }
+          if (i0 + 8 < nq_pad) { r1p[0] += dq[dt][2]; r1p[1] += dq[dt][3]; }
+        }
+      }
+      __syncthreads();
+      // ---------------- phase 2: warp owns keys [warp*16, +16) of this block ----------------
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // contraction over the 64 queries of the block
+        uint32_t pa[4], da[4];
+        ldsm_x4_t(pa, s_u32(Ps + (kk * 16 + (m8 >> 1) * 8 + r8) * PP + (warp * 16 + (m8 & 1) * 8) * 2));
+        ldsm_x4_t(da, s_u32(dSs + (kk * 16 + (m8 >> 1) * 8 + r8) * PP + (warp * 16 + (m8 & 1) * 8) * 2));
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; dt += 2) {
+          uint32_t b[4];
+          ldsm_x4_t(b, s_u32(dOs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+          mma16816(dv[dt], pa, b);
+          mma16816(dv[dt + 1], pa, b + 2);
+          ldsm_x4_t(b, s_u32(Qs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+          mma16816(dk[dt], da, b);
+          mma16816(dk[dt + 1], da, b + 2);
+        }
+      }
+    }
+    // write dK / dV of this key block: rows j0 (g) and j0+8
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int j = kb * BKEY + warp * 16 + g + r * 8;
+      if (j < t.nk) {
+        const size_t gr = (size_t)t.krow[j];
+        if (P.dK_lp != nullptr) {
+#pragma unroll
+          for (int dt = 0; dt < HD / 8; ++dt) {
+            *(uint32_t*)(P.dK_lp + gr * P.lddkv_lp + col0 + dt * 8 + t4 * 2) = pack_bf16(dk[dt][r * 2], dk[dt][r * 2 + 1]);
+            *(uint32_t*)(P.dV_lp + gr * P.lddkv_lp + col0 + dt * 8 + t4 * 2) = pack_bf16(dv[dt][r * 2], dv[dt][r * 2 + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int dt = 0; dt < HD / 8; ++dt) {
+            atomicAdd(P.dK + gr * P.lddk + col0 + dt * 8 + t4 * 2, dk[dt][r * 2]);
+            atomicAdd(P.dK + gr * P.lddk + col0 + dt * 8 + t4 * 2 + 1, dk[dt][r * 2 + 1]);
+            atomicAdd(P.dV + gr * P.lddv + col0 + dt * 8 + t4 * 2, dv[dt][r * 2]);
+            atomicAdd(P.dV + gr * P.lddv + col0 + dt * 8 + t4 * 2 + 1, dv[dt][r * 2 + 1]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // dQ panel -> global bf16 ; bias-table gradient -> global fp32
+  for (int c = threadIdx.x; c < t.nq * (HD / 8); c += blockDim.x) {
+    const int i = c / (HD / 8), ch = c % (HD / 8);
+    const float* src = dQacc + (size_t)i * HD + ch * 8;
+    uint4 v;
+    uint32_t* pv = (uint32_t*)&v;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pv[e] = pack_bf16(src[2 * e], src[2 * e + 1]);
+    *(uint4*)(P.dQ + (size_t)t.qrow[i] * P.lddq + col0 + ch * 8) = v;
+  }
+  if (WINDOW && P.dtable != nullptr)
+    for (int r = threadIdx.x; r < n_rel; r += blockDim.x) {
+      const float v = dtab_s[r];
+      if (v != 0.f) atomicAdd(&P.dtable[(size_t)r * P.win.heads + h], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int pad64(int n) { return (n + 63) / 64 * 64; }
+
+template <int HD, bool WINDOW>
+static size_t table_bytes(const AttnParams& P, int nq_pad, int nk_pad) {
+  if (WINDOW) {
+    const int n_rel = (2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
+    return sizeof(int) * nq_pad + sizeof(short) * nq_pad + (nq_pad + 15) / 16 * 16 + sizeof(float) * n_rel;
+  }
+  return sizeof(int) * (nq_pad + nk_pad) + nk_pad;
+}
+
+template <int HD, bool WINDOW>
+static int launch_fwd(const AttnParams& P, int Pn, int nq, int max_nk, cudaStream_t st) {
+  constexpr int PITCH = HD * 2 + 16;
+  const int nq_pad = pad64(nq), nk_pad = pad64(max_nk);
+  const size_t smem = 3 * 64 * PITCH + table_bytes<HD, WINDOW>(P, nq_pad, nk_pad) + 16;
+  auto kern = attn_mma_fwd_kernel<HD, WINDOW>;
+  if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(nq_pad / 64, Pn, P.H);
+  kern<<<grid, 128, smem, st>>>(P, nq_pad, nk_pad);
+  return check_launch("attn_mma_fwd_kernel");
+}
+
+template <int HD, bool WINDOW>
+static int launch_bwd(const AttnParams& P, int Pn, int nq, int max_nk, cudaStream_t st) {
+  constexpr int PITCH = HD * 2 + 16, PP = 64 * 2 + 16;
+  const int nq_pad = pad64(nq), nk_pad = pad64(max_nk);
+  size_t n_rel = 0;
+  if (WINDOW) n_rel = (size_t)(2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
+  const size_t smem = 4 * 64 * PITCH + 2 * 64 * PP + sizeof(float) * ((size_t)nq_pad * HD + 2 * nq_pad + n_rel) +
+                      table_bytes<HD, WINDOW>(P, nq_pad, nk_pad) + 16;
+  VALOR_REQUIRE(smem <= 227 * 1024, "attn_mma_bwd: %d queries x hd %d need %zu B of shared memory", nq, HD, smem);
+  auto kern = attn_mma_bwd_kernel<HD, WINDOW>;
+  if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(Pn, P.H);
+  kern<<<grid, 128, smem, st>>>(P, nq_pad, nk_pad);
+  return check_launch("attn_mma_bwd_kernel");
+}
+
+bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
+                       const void* k, const void* v, const void* o) {
+  if (dtype != VALOR_DT_BF16 || (hd != 32 && hd != 64)) return false;
+  if ((ldq | ldk | ldv | ldo) % 8) return false;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) return false;
+  return true;
+}
+
+int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
+                long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale,
+                cudaStream_t st) {
+  AttnParams P = {};
+  P.Q = (const bf16*)Q; P.K = (const bf16*)K; P.V = (const bf16*)V; P.ldq = ldq; P.ldk = ldk; P.ldv = ldv;
+  P.O = (bf16*)O; P.ldo = ldo; P.lse = lse; P.H = H; P.hd = hd; P.Nq = Nq; P.max_nk = ix.max_nk; P.scale = scale;
+  P.mha = ix;
+  VALOR_REQUIRE(Pn <= 65535, "mha: too many problems (%d)", Pn);
+  return hd == 32 ? launch_fwd<32, false>(P, Pn, Nq, ix.max_nk, st) : launch_fwd<64, false>(P, Pn, Nq, ix.max_nk, st);
+}
+
+int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ, long long lddq,
+                float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq, float scale,
+                cudaStream_t st) {
+  AttnParams P = {};
+  P.Q = (const bf16*)Q; P.K = (const bf16*)K; P.V = (const bf16*)V; P.ldq = ldq; P.ldk = ldk; P.ldv = ldv;
+  P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.H = H; P.hd = hd; P.Nq = Nq; P.max_nk = ix.max_nk; P.scale = scale;
+  P.dO = (const bf16*)dO; P.dQ = (bf16*)dQ; P.lddq = lddq; P.dK = dK; P.dV = dV; P.lddk = lddk; P.lddv = lddv;
+  P.mha = ix;
+  VALOR_REQUIRE(H <= 65535, "mha: too many heads");
+  return hd == 32 ? launch_bwd<32, false>(P, Pn, Nq, ix.max_nk, st) : launch_bwd<64, false>(P, Pn, Nq, ix.max_nk, st);
+}
+
+int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
+                   int H, int hd, float scale, cudaStream_t st) {
+  const int C = H * hd;
+  AttnParams P = {};
+  P.Q = (const bf16*)qkv; P.K = P.Q + C; P.V = P.Q + 2 * C; P.ldq = P.ldk = P.ldv = ld;
+  P.O = (bf16*)O; P.ldo = ldo; P.lse = lse; P.H = H; P.hd = hd; P.Nq = ix.N; P.max_nk = ix.N; P.scale = scale;
+  P.win = ix;
+  VALOR_REQUIRE(Pn <= 65535, "window_attn: too many windows (%d)", Pn);
+  return hd == 32 ? launch_fwd<32, true>(P, Pn, ix.N, ix.N, st) : launch_fwd<64, true>(P, Pn, ix.N, ix.N, st);
+}
+
+int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
+                   const float* lse, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd, float scale,
+                   cudaStream_t st) {
+  const int C = H * hd;
+  AttnParams P = {};
+  P.Q = (const bf16*)qkv; P.K = P.Q + C; P.V = P.Q + 2 * C; P.ldq = P.ldk = P.ldv = ld;
+  P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.H = H; P.hd = hd; P.Nq = ix.N; P.max_nk = ix.N; P.scale = scale;
+  P.dO = (const bf16*)dO; P.dQ = (bf16*)dqkv; P.lddq = lddq;
+  P.dK_lp = (bf16*)dqkv + C; P.dV_lp = (bf16*)dqkv + 2 * C; P.lddkv_lp = lddq;
+  P.dtable = dtable;
+  P.win = ix;
+  VALOR_REQUIRE(H <= 65535, "window_attn: too many heads");
+  return hd == 32 ? launch_bwd<32, true>(P, Pn, ix.N, ix.N, st) : launch_bwd<64, true>(P, Pn, ix.N, ix.N, st);
+}
+
+}  // namespace valor

@@ -158,14 +158,12 @@ def window_attn_bwd(qkv, o, do, lse, table, dtable, grid, win, shift, cfg_win, h
                     backend=BACKEND_AUTO):
     """returns dqkv [tokens, 3C] in qkv.dtype; dtable (fp32) accumulated in place."""
     B, D, H, W = grid
-    C = heads * hd
     dqkv = torch.empty_like(qkv)
-    dkv = torch.zeros(qkv.shape[0], 2 * C, device=qkv.device, dtype=torch.float32)
     do = do.contiguous()
+    nbytes = _lib.load().valor_window_attn_bwd_scratch_bytes(DT(qkv), qkv.shape[0], heads, hd, _ld(qkv), backend)
+    scratch = torch.zeros(nbytes // 4, device=qkv.device, dtype=torch.float32) if nbytes else None
     _call("valor_window_attn_bwd", DT(qkv), P(qkv), _ld(qkv), P(o), P(do), _ld(o), P(lse), P(table), P(dqkv),
-          _ld(dqkv), P(dkv[:, :C]), P(dkv[:, C:]), _ld(dkv), P(dtable), B, D, H, W, *win, *shift, *cfg_win, heads, hd,
-          float(scale), backend, ST())
-    cast2d(dkv, dqkv[:, C:])
+          _ld(dqkv), P(scratch), P(dtable), B, D, H, W, *win, *shift, *cfg_win, heads, hd, float(scale), backend, ST())
     return dqkv
 
 
