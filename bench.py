@@ -33,6 +33,13 @@ TASK = "pt_contra%tva%tv%ta_caption%tva%tv%ta"
 FLOPS_PER_SAMPLE = 1178.8e9  # fwd+bwd matmul FLOPs / sample at F8 A2 T32
 
 
+T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench {time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -46,6 +53,7 @@ def parse():
     ap.add_argument("--geom", default="base", choices=["base", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -133,7 +141,9 @@ def cpu_step_fn(geom, B, F, A, T):
 
 def cpu_baseline(geom, F, A, T, steps=2, warmup=1, B=2):
     import torch
-    torch.set_num_threads(os.cpu_count())
+    # all host cores up to 32: the oracle issues thousands of small ATen ops per step and
+    # oversubscribes badly beyond that (a 200+-thread OpenMP team per op is slower, not faster)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
     run = cpu_step_fn(geom, B, F, A, T)
     for _ in range(warmup):
         run()
@@ -240,22 +250,76 @@ def main():
             ms = t.item()
         return ms / steps, out
 
-    for _ in range(max(args.warmup, 3)):
+    log("model + batch ready")
+    for i in range(2):
         train_step(resident)
+        torch.cuda.synchronize()
+        log(f"eager warmup step {i} done")
+    # ---- capture the whole step (forward, backward, all-reduce, clip, AdamW) in one CUDA graph: the C ABI
+    # never syncs or allocates, so ~2000 launches replay without Python / launch latency
+    graph = None
+    eager_step = train_step
+    if not args.no_graph:
+        try:
+            def body(batch):
+                store.zero_grad()
+                losses = model(batch, TASK, compute_loss=True)
+                sum(losses.values()).backward()
+                allreduce_grads(store)
+                store.optimizer_step(max_norm=opts.grad_norm)
+                return losses
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body(resident)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l_before = K.launch_count
+            with torch.cuda.graph(graph):
+                static_losses = body(resident)
+            graph_launches = K.launch_count - l_before
+
+            def train_step(batch):  # noqa: F811  (batch must be `resident`: static input tensors)
+                gstep[0] += 1
+                store.set_hyper(get_lr_sched(gstep[0], opts), base_lr=opts.learning_rate, betas=tuple(opts.betas),
+                                weight_decay=opts.weight_decay)
+                graph.replay()
+                return static_losses
+            log(f"CUDA graph captured: {graph_launches} ABI launches per step")
+        except Exception as ex:  # pragma: no cover
+            log(f"CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly")
+            graph = None
+            train_step = eager_step
+            torch.cuda.synchronize()
+    for i in range(max(args.warmup, 3)):
+        train_step(resident)
+        torch.cuda.synchronize()
+        log(f"warmup step {i} done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = K.launch_count
     ms_step, losses = timed(lambda: train_step(resident), args.steps)
-    launches = (K.launch_count - l0) // args.steps
+    launches = graph_launches if graph is not None else (K.launch_count - l0) // args.steps
+    log(f"timed: {ms_step:.2f} ms/step, {launches} launches/step")
 
     def e2e_step():
-        losses = train_step(to_device())
+        if graph is not None:   # H2D from pinned host memory INTO the graph's static input tensors
+            resident["video_pixels"].copy_(pinned["video"], non_blocking=True)
+            resident["audio_spectrograms"].copy_(pinned["audio"], non_blocking=True)
+            resident["txt_tokens"]["bert_tokens"].copy_(pinned["tokens"], non_blocking=True)
+            resident["caption_mask"][0].copy_(pinned["mi"], non_blocking=True)
+            resident["caption_mask"][1].copy_(pinned["ml"], non_blocking=True)
+            losses = train_step(resident)
+        else:
+            losses = train_step(to_device())
         return {k: v.item() for k, v in losses.items()}     # D2H read of the step's result
 
     e2e_step()
     ms_e2e, loss_vals = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    log(f"e2e: {ms_e2e:.2f} ms/step")
 
     # ---- roofline pass: CUDA events around every GEMM launch of one more step (outside the timed region)
     roof = None
@@ -277,7 +341,7 @@ def main():
 
         K.gemm = gemm_probe
         try:
-            train_step(resident)
+            eager_step(resident)
             torch.cuda.synchronize()
         finally:
             K.gemm = orig
@@ -302,12 +366,14 @@ def main():
                        "geom": args.geom},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4 * len(loss_vals)},
-            "gpu_launches": launches, "clocks": clocks, "losses": loss_vals,
+            "gpu_launches": launches, "cuda_graph": graph is not None, "clocks": clocks, "losses": loss_vals,
             "step_mfu": FLOPS_PER_SAMPLE * B / (ms_step * 1e-3) / (peak_tf * 1e12) if args.geom == "base" else None}
     if roof:
         line["roofline"] = roof
+    log("roofline pass done")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(geom, F, A, T, steps=2, warmup=1)
+        log("cpu baseline done")
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line))

@@ -69,8 +69,10 @@ int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void
  * apex/csrc/layer_norm_cuda_kernel.cu) and nn.LayerNorm (videoswin.py:181,187,252,439) ------- */
 int valor_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
                         float* rstd, long long M, int N, float eps, void* stream);
+/* dres (optional): gradient that reaches x through a residual branch bypassing the LN; dx = LN'(dy) + dres */
 int valor_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma, const float* mean,
-                        const float* rstd, void* dx, float* dgamma, float* dbeta, long long M, int N, void* stream);
+                        const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, long long M,
+                        int N, void* stream);
 
 /* ---- F.normalize(dim=-1) on contrastive features (pretrain.py:276,283,289) -------------------- */
 int valor_l2norm_fwd(int dtype, const void* x, void* y, float* nrm, long long M, int N, void* stream);
@@ -84,15 +86,16 @@ int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm,
  * scores = q.k^T * scale + mask, mask = -10000 where key_valid[p,j]==0 or (causal[p] && j>i)
  * (bert.py:869-885).  lse [P,H,Nq] fp32 is saved for the backward.
  * Backward: dQ written; dK/dV accumulated with += into fp32 [rows, H*hd] buffers the caller
- * zero-fills (K/V rows shared by several problems add up). */
+ * zero-fills (K/V rows shared by several problems add up); `delta` is a [P,H,Nq] fp32 scratch
+ * (rowsum(dO*O), produced by the dQ kernel and consumed by the dK/dV kernel). */
 int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
                   void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid, const unsigned char* causal,
                   float scale, int backend, void* stream);
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
-                  long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ,
-                  long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd, int Nq,
-                  int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
+                  long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta,
+                  void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd,
+                  int Nq, int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
                   const unsigned char* key_valid, const unsigned char* causal, float scale, int backend, void* stream);
 
 /* ---- VideoSwin shifted-window attention: WindowAttention3D.forward (videoswin.py:137-163)
@@ -109,8 +112,8 @@ int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, lon
                           int sw, int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream);
 long long valor_window_attn_bwd_scratch_bytes(int dtype, long long tokens, int heads, int hd, long long ld, int backend);
 int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
-                          const float* lse, const float* table, void* dqkv, long long lddqkv, float* scratch,
-                          float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
+                          const float* lse, float* delta, const float* table, void* dqkv, long long lddqkv,
+                          float* scratch, float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
                           int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream);
 
 /* ---- data movement around the GEMMs --------------------------------------------------------- */

@@ -72,7 +72,7 @@ def layernorm_fwd(x, gamma, beta, eps):
     return y.to(x.dtype), mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
     dyf, xf = dy.float(), x.float()
     xh = (xf - mean[:, None]) * rstd[:, None]
     if dgamma is not None:
@@ -81,6 +81,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
         dbeta += dyf.sum(0)
     g = dyf * gamma
     dx = (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True)) * rstd[:, None]
+    if dres is not None:
+        dx = dx + dres.float()
     return dx.to(x.dtype)
 
 

@@ -148,6 +148,9 @@ def test_layernorm(dtype, M, N):
         dx_r = R.layernorm_bwd(dy, x, g, mean_r, rstd_r, dg_r, db_r)
         dg, db = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
         dx = k.layernorm_bwd(dev(dy, dtype), dev(x, dtype), dev(g), mean, rstd, dg, db)
+        dres = rnd(M, N, dtype=dtype, seed=9)
+        dx2 = k.layernorm_bwd(dev(dy, dtype), dev(x, dtype), dev(g), mean, rstd, torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda"), dres=dev(dres, dtype))
+        close(dx2, dx_r.float() + dres, dtype, "ln dx + residual grad")
         close(dx, dx_r, dtype, "ln dx")
         close(dg, dg_r, dtype, "ln dgamma")
         close(db, db_r, dtype, "ln dbeta")

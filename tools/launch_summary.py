@@ -1,0 +1,35 @@
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel name."""
+import csv
+import re
+import sys
+from collections import defaultdict
+
+
+def main(path, skip=0, top=40):
+    rows = []
+    with open(path, newline="") as f:
+        lines = [l for l in f if not l.startswith("==")]
+    rd = csv.reader(lines)
+    hdr = next(rd)
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    for r in rd:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        u = r[ui]
+        us = v / 1000.0 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1000.0 if u in ("ms", "msecond") else v)
+        rows.append((r[ki], us))
+    rows = rows[skip:]
+    agg = defaultdict(lambda: [0, 0.0])
+    for k, us in rows:
+        name = re.sub(r"\(.*", "", k).replace("void ", "").replace("valor::", "")
+        agg[name][0] += 1
+        agg[name][1] += us
+    total = sum(v[1] for v in agg.values())
+    print(f"launches {len(rows)}  total {total/1000:.2f} ms")
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"{us/1000:9.3f} ms {100*us/total:5.1f}%  n={n:5d}  avg {us/n:9.1f} us  {name[:110]}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)

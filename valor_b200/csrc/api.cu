@@ -30,7 +30,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
 int gemm_simt(int dtype, const void* A, long long sam, long long sak, const void* B, long long sbn, long long sbk,
               void* C, long long ldc, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st);
 int layernorm_fwd(int, const void*, const float*, const float*, void*, float*, float*, long long, int, float, cudaStream_t);
-int layernorm_bwd(int, const void*, const void*, const float*, const float*, const float*, void*, float*, float*, long long, int, cudaStream_t);
+int layernorm_bwd(int, const void*, const void*, const float*, const float*, const float*, const void*, void*, float*, float*, long long, int, cudaStream_t);
 int l2norm_fwd(int, const void*, void*, float*, long long, int, cudaStream_t);
 int l2norm_bwd(int, const void*, const void*, const float*, void*, long long, int, cudaStream_t);
 int swin_im2col(int, int, const void*, void*, int, int, int, int, cudaStream_t);
@@ -64,12 +64,14 @@ bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long lon
 int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
                 long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
 int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
-                long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ, long long lddq,
-                float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
+                long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta, void* dQ,
+                long long lddq, float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq,
+                float scale, cudaStream_t st);
 int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
                    int H, int hd, float scale, cudaStream_t st);
 int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
-                   const float* lse, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd, float scale, cudaStream_t st);
+                   const float* lse, float* delta, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd,
+                   float scale, cudaStream_t st);
 
 }  // namespace valor
 
@@ -111,8 +113,9 @@ int valor_layernorm_fwd(int dtype, const void* x, const float* gamma, const floa
   return layernorm_fwd(dtype, x, gamma, beta, y, mean, rstd, M, N, eps, ST);
 }
 int valor_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma, const float* mean,
-                        const float* rstd, void* dx, float* dgamma, float* dbeta, long long M, int N, void* stream) {
-  return layernorm_bwd(dtype, dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, N, ST);
+                        const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, long long M, int N,
+                        void* stream) {
+  return layernorm_bwd(dtype, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, M, N, ST);
 }
 int valor_l2norm_fwd(int dtype, const void* x, void* y, float* nrm, long long M, int N, void* stream) {
   return l2norm_fwd(dtype, x, y, nrm, M, N, ST);
@@ -141,17 +144,17 @@ int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long l
   return mha_ref_fwd(dtype, ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, ST);
 }
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
-                  long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ,
-                  long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd, int Nq,
-                  int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
+                  long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta,
+                  void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd,
+                  int Nq, int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
                   const unsigned char* key_valid, const unsigned char* causal, float scale, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
   const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O) && (lddq % 8 == 0) &&
-                  (((uintptr_t)dQ | (uintptr_t)dO) & 15) == 0 && Nq <= 448;
+                  (((uintptr_t)dQ | (uintptr_t)dO) & 15) == 0 && delta != nullptr;
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_bwd: tensor backend requested but not eligible");
   if (backend != VALOR_BACKEND_SIMT && ok)
-    return mha_mma_bwd(ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq, scale, ST);
+    return mha_mma_bwd(ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, delta, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq, scale, ST);
   return mha_ref_bwd(dtype, ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq,
                      scale, ST);
 }
@@ -190,8 +193,8 @@ long long valor_window_attn_bwd_scratch_bytes(int dtype, long long tokens, int h
   return tokens * 2LL * heads * hd * (long long)sizeof(float);
 }
 int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
-                          const float* lse, const float* table, void* dqkv, long long lddqkv, float* scratch,
-                          float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
+                          const float* lse, float* delta, const float* table, void* dqkv, long long lddqkv,
+                          float* scratch, float* dtable, int B, int D, int H, int W, int wd, int wh, int ww, int sd, int sh, int sw,
                           int WD, int WH, int WW, int heads, int hd, float scale, int backend, void* stream) {
   WindowIndex ix;
   if (make_window(ix, table, B, D, H, W, wd, wh, ww, sd, sh, sw, WD, WH, WW, heads)) return 1;
@@ -199,8 +202,8 @@ int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* 
   const int C = heads * hd;
   const long long tokens = (long long)B * D * H * W;
   if (window_bwd_tensor_ok(dtype, hd, ld, backend) && lddqkv % 8 == 0 && ldo % 8 == 0 &&
-      ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) && ix.N <= 448)
-    return window_mma_bwd(ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);
+      ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) && delta != nullptr)
+    return window_mma_bwd(ix, qkv, ld, O, dO, ldo, lse, delta, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);
   VALOR_REQUIRE(scratch != nullptr, "valor_window_attn_bwd: SIMT path needs the fp32 scratch buffer");
   if (window_ref_bwd(dtype, ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, scratch, scratch + C, 2 * C, dtable, P, heads,
                      hd, scale, ST))

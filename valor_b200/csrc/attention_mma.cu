@@ -266,209 +266,262 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
 }
 
 // ==========================================================================================
-// backward: one CTA per (problem, head); 128 threads.
-//   outer loop: key blocks (dK/dV of 16 keys per warp live in registers)
-//   inner loop: query blocks; phase 1 warps own queries (S, P, dP, dS, dQ), phase 2 warps own
-//   keys (dV += P^T dO, dK += dS^T Q) after P / dS went through shared memory.
-//   dQ accumulates in a shared-memory fp32 panel (rows owned by one warp at a time).
+// backward, split in two forward-shaped kernels (small shared-memory footprint -> many CTAs per
+// SM hide the gather latency; no cross-warp accumulation panels, no P/dS round trip):
+//   dq  kernel: CTA = 64 queries; loops key blocks;  S, P, dP, dS in registers, dQ += dS.K,
+//               delta = rowsum(dO*O) computed here and published for the dkv kernel,
+//               relative-position-bias gradient via shared-memory atomics (window case)
+//   dkv kernel: CTA = 64 keys;    loops query blocks; S^T = K.Q^T etc. so that P^T / dS^T come out
+//               of the MMA already in A-operand layout: dV += P^T.dO, dK += dS^T.Q
 // ==========================================================================================
 template <int HD, bool WINDOW>
 __global__ void __launch_bounds__(128)
-attn_mma_bwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
-  constexpr int PITCH = HD * 2 + 16, PP = 64 * 2 + 16;
+attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int nk_pad) {
+  constexpr int PITCH = HD * 2 + 16;
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* Qs = smem;
   unsigned char* dOs = Qs + 64 * PITCH;
   unsigned char* Ks = dOs + 64 * PITCH;
   unsigned char* Vs = Ks + 64 * PITCH;
-  unsigned char* Ps = Vs + 64 * PITCH;
-  unsigned char* dSs = Ps + 64 * PP;
-  float* dQacc = (float*)(dSs + 64 * PP);       // [nq_pad][HD]
-  float* lse_s = dQacc + (size_t)nq_pad * HD;    // [nq_pad]
-  float* del_s = lse_s + nq_pad;                 // [nq_pad]
-  float* dtab_s = del_s + nq_pad;                // window: [n_rel]
-  const int p = blockIdx.x, h = blockIdx.y;
+  float* lse_s = (float*)(Vs + 64 * PITCH);  // [64]
+  float* del_s = lse_s + 64;                 // [64]
+  float* dtab_s = del_s + 64;                // window: [n_rel]
+  const int p = blockIdx.y, h = blockIdx.z, qb = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   int n_rel = 0;
   if (WINDOW) n_rel = (2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
   Tables t;
   build_tables<WINDOW>(t, (unsigned char*)(dtab_s + n_rel), P, p, h, nq_pad, nk_pad);
-  for (int i = threadIdx.x; i < nq_pad * HD; i += blockDim.x) dQacc[i] = 0.f;
   for (int i = threadIdx.x; i < n_rel; i += blockDim.x) dtab_s[i] = 0.f;
   __syncthreads();
   const int col0 = h * HD;
-  // lse and delta = rowsum(dO * O) per query
-  for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {
-    float l = 0.f, d = 0.f;
-    if (i < t.nq) {
-      l = P.lse[((size_t)p * P.H + h) * P.Nq + i];
-      const bf16* orow = P.O + (size_t)t.qrow[i] * P.ldo + col0;
-      const bf16* drow = P.dO + (size_t)t.qrow[i] * P.ldo + col0;
+  load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
+  load_tile<HD>(dOs, P.dO, P.ldo, col0, t.qrow, qb * BQ);
+  load_tile<HD>(Ks, P.O, P.ldo, col0, t.qrow, qb * BQ);  // O tile, only for delta
+  __syncthreads();
+  {  // delta_i = sum_d dO[i,d] * O[i,d] : two threads per row
+    const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
+    float d = 0.f;
+    const __nv_bfloat162* a = (const __nv_bfloat162*)(dOs + r * PITCH + hf * HD);
+    const __nv_bfloat162* b = (const __nv_bfloat162*)(Ks + r * PITCH + hf * HD);
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
-        const uint4 a = *(const uint4*)(orow + c), b = *(const uint4*)(drow + c);
-        const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
-        const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
-          d += fa.x * fb.x + fa.y * fb.y;
-        }
-      }
+    for (int c = 0; c < HD / 4; ++c) {
+      const float2 fa = __bfloat1622float2(a[c]), fb = __bfloat1622float2(b[c]);
+      d += fa.x * fb.x + fa.y * fb.y;
     }
-    lse_s[i] = l;
-    del_s[i] = d;
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    const int i = qb * BQ + r;
+    if (hf == 0) {
+      del_s[r] = d;
+      lse_s[r] = i < t.nq ? P.lse[((size_t)p * P.H + h) * P.Nq + i] : 0.f;
+      if (i < t.nq) delta[((size_t)p * P.H + h) * P.Nq + i] = d;
+    }
   }
-  const float sc = P.scale;
-  const int nkb = (t.nk + BKEY - 1) / BKEY, nqb = (t.nq + BQ - 1) / BQ;
   const int m8 = lane >> 3, r8 = lane & 7;
+  uint32_t qf[HD / 16][4], dof[HD / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    ldsm_x4(qf[ks], s_u32(Qs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+    ldsm_x4(dof[ks], s_u32(dOs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+  }
+  float dq[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const float sc = P.scale;
+  const int il = warp * 16 + g;
+  const int i0 = qb * BQ + il;
+  const int nkb = (t.nk + BKEY - 1) / BKEY;
   for (int kb = 0; kb < nkb; ++kb) {
     __syncthreads();
     load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
     load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
-    float dk[HD / 8][4], dv[HD / 8][4];
+    __syncthreads();
+    float s[8][4], dp[8][4];
 #pragma unroll
-    for (int i = 0; i < HD / 8; ++i)
+    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
-    for (int qb = 0; qb < nqb; ++qb) {
-      __syncthreads();
-      load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
-      load_tile<HD>(dOs, P.dO, P.ldo, col0, t.qrow, qb * BQ);
-      __syncthreads();
-      // ---------------- phase 1: warp owns queries [warp*16, +16) of this block ----------------
-      {
-        uint32_t qf[HD / 16][4], dof[HD / 16][4];
+      for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
-          ldsm_x4(qf[ks], s_u32(Qs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
-          ldsm_x4(dof[ks], s_u32(dOs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
-        }
-        float s[8][4], dp[8][4];
+    for (int ks = 0; ks < HD / 16; ++ks)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-#pragma unroll
-          for (int nt = 0; nt < 8; nt += 2) {
-            uint32_t b[4];
-            ldsm_x4(b, s_u32(Ks + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-            mma16816(s[nt], qf[ks], b);
-            mma16816(s[nt + 1], qf[ks], b + 2);
-            ldsm_x4(b, s_u32(Vs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-            mma16816(dp[nt], dof[ks], b);
-            mma16816(dp[nt + 1], dof[ks], b + 2);
-          }
-        const int il = warp * 16 + g;            // local rows il, il+8 within the q block
-        const int i0 = qb * BQ + il;
-        uint32_t dsf[4][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          float pv[4], ds[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = i0 + (e >> 1) * 8, j = kb * BKEY + nt * 8 + t4 * 2 + (e & 1);
-            float pr = 0.f, d = 0.f;
-            if (i < t.nq && j < t.nk) {
-              const float sv = s[nt][e] * sc + add_term<WINDOW>(t, i, j);
-              pr = __expf(sv - lse_s[i]);
-              d = pr * (dp[nt][e] - del_s[i]);
-              if (WINDOW) atomicAdd(&dtab_s[t.code[i] - t.code[j] + t.center], d);
-            }
-            pv[e] = pr;
-            ds[e] = d * sc;
-          }
-          // P and dS (bf16) to shared memory, [query][key]
-          *(uint32_t*)(Ps + il * PP + (nt * 8 + t4 * 2) * 2) = pack_bf16(pv[0], pv[1]);
-          *(uint32_t*)(Ps + (il + 8) * PP + (nt * 8 + t4 * 2) * 2) = pack_bf16(pv[2], pv[3]);
-          const uint32_t d01 = pack_bf16(ds[0], ds[1]), d23 = pack_bf16(ds[2], ds[3]);
-          *(uint32_t*)(dSs + il * PP + (nt * 8 + t4 * 2) * 2) = d01;
-          *(uint32_t*)(dSs + (il + 8) * PP + (nt * 8 + t4 * 2) * 2) = d23;
-          dsf[nt >> 1][(nt & 1) * 2 + 0] = d01;
-          dsf[nt >> 1][(nt & 1) * 2 + 1] = d23;
-        }
-        // dQ_w += dS_w . K_blk
-        float dq[HD / 8][4];
-#pragma unroll
-        for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-          for (int dt = 0; dt < HD / 8; dt += 2) {
-            uint32_t b[4];
-            ldsm_x4_t(b, s_u32(Ks + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-            mma16816(dq[dt], dsf[kk], b);
-            mma16816(dq[dt + 1], dsf[kk], b + 2);
-          }
-#pragma unroll
-        for (int dt = 0; dt < HD / 8; ++dt) {
-          float* r0p = dQacc + (size_t)(i0)*HD + dt * 8 + t4 * 2;
-          float* r1p = dQacc + (size_t)(i0 + 8) * HD + dt * 8 + t4 * 2;
-          if (i0 < nq_pad) { r0p[0] += dq[dt][0]; r0p[1] += dq[dt][1]; }
-          if (i0 + 8 < nq_pad) { r1p[0] += dq[dt][2]; r1p[1] += dq[dt][3]; }
-        }
+      for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t b[4];
+        ldsm_x4(b, s_u32(Ks + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+        mma16816(s[nt], qf[ks], b);
+        mma16816(s[nt + 1], qf[ks], b + 2);
+        ldsm_x4(b, s_u32(Vs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+        mma16816(dp[nt], dof[ks], b);
+        mma16816(dp[nt + 1], dof[ks], b + 2);
       }
-      __syncthreads();
-      // ---------------- phase 2: warp owns keys [warp*16, +16) of this block ----------------
+    uint32_t dsf[4][4];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {  // contraction over the 64 queries of the block
-        uint32_t pa[4], da[4];
-        ldsm_x4_t(pa, s_u32(Ps + (kk * 16 + (m8 >> 1) * 8 + r8) * PP + (warp * 16 + (m8 & 1) * 8) * 2));
-        ldsm_x4_t(da, s_u32(dSs + (kk * 16 + (m8 >> 1) * 8 + r8) * PP + (warp * 16 + (m8 & 1) * 8) * 2));
+    for (int nt = 0; nt < 8; ++nt) {
+      float ds[4];
 #pragma unroll
-        for (int dt = 0; dt < HD / 8; dt += 2) {
-          uint32_t b[4];
-          ldsm_x4_t(b, s_u32(dOs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-          mma16816(dv[dt], pa, b);
-          mma16816(dv[dt + 1], pa, b + 2);
-          ldsm_x4_t(b, s_u32(Qs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-          mma16816(dk[dt], da, b);
-          mma16816(dk[dt + 1], da, b + 2);
+      for (int e = 0; e < 4; ++e) {
+        const int rr = (e >> 1) * 8;
+        const int i = i0 + rr, j = kb * BKEY + nt * 8 + t4 * 2 + (e & 1);
+        float d = 0.f;
+        if (i < t.nq && j < t.nk) {
+          const float sv = s[nt][e] * sc + add_term<WINDOW>(t, i, j);
+          const float pr = __expf(sv - lse_s[il + rr]);
+          d = pr * (dp[nt][e] - del_s[il + rr]);
+          if (WINDOW) atomicAdd(&dtab_s[t.code[i] - t.code[j] + t.center], d);
         }
+        ds[e] = d * sc;
       }
+      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
+      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
     }
-    // write dK / dV of this key block: rows j0 (g) and j0+8
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int j = kb * BKEY + warp * 16 + g + r * 8;
-      if (j < t.nk) {
-        const size_t gr = (size_t)t.krow[j];
-        if (P.dK_lp != nullptr) {
+    for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-          for (int dt = 0; dt < HD / 8; ++dt) {
-            *(uint32_t*)(P.dK_lp + gr * P.lddkv_lp + col0 + dt * 8 + t4 * 2) = pack_bf16(dk[dt][r * 2], dk[dt][r * 2 + 1]);
-            *(uint32_t*)(P.dV_lp + gr * P.lddkv_lp + col0 + dt * 8 + t4 * 2) = pack_bf16(dv[dt][r * 2], dv[dt][r * 2 + 1]);
-          }
-        } else {
-#pragma unroll
-          for (int dt = 0; dt < HD / 8; ++dt) {
-            atomicAdd(P.dK + gr * P.lddk + col0 + dt * 8 + t4 * 2, dk[dt][r * 2]);
-            atomicAdd(P.dK + gr * P.lddk + col0 + dt * 8 + t4 * 2 + 1, dk[dt][r * 2 + 1]);
-            atomicAdd(P.dV + gr * P.lddv + col0 + dt * 8 + t4 * 2, dv[dt][r * 2]);
-            atomicAdd(P.dV + gr * P.lddv + col0 + dt * 8 + t4 * 2 + 1, dv[dt][r * 2 + 1]);
-          }
-        }
+      for (int dt = 0; dt < HD / 8; dt += 2) {
+        uint32_t b[4];
+        ldsm_x4_t(b, s_u32(Ks + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+        mma16816(dq[dt], dsf[kk], b);
+        mma16816(dq[dt + 1], dsf[kk], b + 2);
       }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + r * 8;
+    if (i < t.nq) {
+      bf16* dst = P.dQ + (size_t)t.qrow[i] * P.lddq + col0;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt)
+        *(uint32_t*)(dst + dt * 8 + t4 * 2) = pack_bf16(dq[dt][r * 2], dq[dt][r * 2 + 1]);
     }
   }
-  __syncthreads();
-  // dQ panel -> global bf16 ; bias-table gradient -> global fp32
-  for (int c = threadIdx.x; c < t.nq * (HD / 8); c += blockDim.x) {
-    const int i = c / (HD / 8), ch = c % (HD / 8);
-    const float* src = dQacc + (size_t)i * HD + ch * 8;
-    uint4 v;
-    uint32_t* pv = (uint32_t*)&v;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) pv[e] = pack_bf16(src[2 * e], src[2 * e + 1]);
-    *(uint4*)(P.dQ + (size_t)t.qrow[i] * P.lddq + col0 + ch * 8) = v;
-  }
-  if (WINDOW && P.dtable != nullptr)
+  if (WINDOW && P.dtable != nullptr) {
+    __syncthreads();
     for (int r = threadIdx.x; r < n_rel; r += blockDim.x) {
       const float v = dtab_s[r];
       if (v != 0.f) atomicAdd(&P.dtable[(size_t)r * P.win.heads + h], v);
     }
+  }
+}
+
+template <int HD, bool WINDOW>
+__global__ void __launch_bounds__(128)
+attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pad, int nk_pad) {
+  constexpr int PITCH = HD * 2 + 16;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* Ks = smem;
+  unsigned char* Vs = Ks + 64 * PITCH;
+  unsigned char* Qs = Vs + 64 * PITCH;
+  unsigned char* dOs = Qs + 64 * PITCH;
+  float* lse_s = (float*)(dOs + 64 * PITCH);  // [nq_pad]
+  float* del_s = lse_s + nq_pad;              // [nq_pad]
+  const int p = blockIdx.y, h = blockIdx.z, kb = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  Tables t;
+  build_tables<WINDOW>(t, (unsigned char*)(del_s + nq_pad), P, p, h, nq_pad, nk_pad);
+  __syncthreads();
+  if (kb * BKEY >= t.nk) return;  // cross-attention: shorter key ranges than max_nk
+  const int col0 = h * HD;
+  for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {
+    const bool ok = i < t.nq;
+    lse_s[i] = ok ? P.lse[((size_t)p * P.H + h) * P.Nq + i] : 0.f;
+    del_s[i] = ok ? delta[((size_t)p * P.H + h) * P.Nq + i] : 0.f;
+  }
+  load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
+  load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
+  __syncthreads();
+  const int m8 = lane >> 3, r8 = lane & 7;
+  uint32_t kf[HD / 16][4], vf[HD / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    ldsm_x4(kf[ks], s_u32(Ks + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+    ldsm_x4(vf[ks], s_u32(Vs + (warp * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+  }
+  float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
+  const float sc = P.scale;
+  const int j0 = kb * BKEY + warp * 16 + g;  // keys j0 and j0+8
+  const int nqb = (t.nq + BQ - 1) / BQ;
+  for (int qb = 0; qb < nqb; ++qb) {
+    __syncthreads();
+    load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
+    load_tile<HD>(dOs, P.dO, P.ldo, col0, t.qrow, qb * BQ);
+    __syncthreads();
+    float s[8][4], dp[8][4];  // rows = keys (g, g+8), cols = queries of this block
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t b[4];
+        ldsm_x4(b, s_u32(Qs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+        mma16816(s[nt], kf[ks], b);
+        mma16816(s[nt + 1], kf[ks], b + 2);
+        ldsm_x4(b, s_u32(dOs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+        mma16816(dp[nt], vf[ks], b);
+        mma16816(dp[nt + 1], vf[ks], b + 2);
+      }
+    uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float pv[4], ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + (e >> 1) * 8;
+        const int i = qb * BQ + nt * 8 + t4 * 2 + (e & 1);
+        float pr = 0.f, d = 0.f;
+        if (i < t.nq && j < t.nk) {
+          const float sv = s[nt][e] * sc + add_term<WINDOW>(t, i, j);
+          pr = __expf(sv - lse_s[i]);
+          d = pr * (dp[nt][e] - del_s[i]);
+        }
+        pv[e] = pr;
+        ds[e] = d * sc;
+      }
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
+      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)  // contraction over the 64 queries of the block
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; dt += 2) {
+        uint32_t b[4];
+        ldsm_x4_t(b, s_u32(dOs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+        mma16816(dv[dt], pf[kk], b);
+        mma16816(dv[dt + 1], pf[kk], b + 2);
+        ldsm_x4_t(b, s_u32(Qs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+        mma16816(dk[dt], dsf[kk], b);
+        mma16816(dk[dt + 1], dsf[kk], b + 2);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = j0 + r * 8;
+    if (j < t.nk) {
+      const size_t gr = (size_t)t.krow[j];
+      if (P.dK_lp != nullptr) {
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; ++dt) {
+          *(uint32_t*)(P.dK_lp + gr * P.lddkv_lp + col0 + dt * 8 + t4 * 2) = pack_bf16(dk[dt][r * 2], dk[dt][r * 2 + 1]);
+          *(uint32_t*)(P.dV_lp + gr * P.lddkv_lp + col0 + dt * 8 + t4 * 2) = pack_bf16(dv[dt][r * 2], dv[dt][r * 2 + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; ++dt) {
+          atomicAdd(P.dK + gr * P.lddk + col0 + dt * 8 + t4 * 2, dk[dt][r * 2]);
+          atomicAdd(P.dK + gr * P.lddk + col0 + dt * 8 + t4 * 2 + 1, dk[dt][r * 2 + 1]);
+          atomicAdd(P.dV + gr * P.lddv + col0 + dt * 8 + t4 * 2, dv[dt][r * 2]);
+          atomicAdd(P.dV + gr * P.lddv + col0 + dt * 8 + t4 * 2 + 1, dv[dt][r * 2 + 1]);
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -498,19 +551,28 @@ static int launch_fwd(const AttnParams& P, int Pn, int nq, int max_nk, cudaStrea
 }
 
 template <int HD, bool WINDOW>
-static int launch_bwd(const AttnParams& P, int Pn, int nq, int max_nk, cudaStream_t st) {
-  constexpr int PITCH = HD * 2 + 16, PP = 64 * 2 + 16;
+static int launch_bwd(const AttnParams& P, float* delta, int Pn, int nq, int max_nk, cudaStream_t st) {
+  constexpr int PITCH = HD * 2 + 16;
   const int nq_pad = pad64(nq), nk_pad = pad64(max_nk);
   size_t n_rel = 0;
   if (WINDOW) n_rel = (size_t)(2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
-  const size_t smem = 4 * 64 * PITCH + 2 * 64 * PP + sizeof(float) * ((size_t)nq_pad * HD + 2 * nq_pad + n_rel) +
-                      table_bytes<HD, WINDOW>(P, nq_pad, nk_pad) + 16;
-  VALOR_REQUIRE(smem <= 227 * 1024, "attn_mma_bwd: %d queries x hd %d need %zu B of shared memory", nq, HD, smem);
-  auto kern = attn_mma_bwd_kernel<HD, WINDOW>;
-  if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(Pn, P.H);
-  kern<<<grid, 128, smem, st>>>(P, nq_pad, nk_pad);
-  return check_launch("attn_mma_bwd_kernel");
+  const size_t tb = table_bytes<HD, WINDOW>(P, nq_pad, nk_pad);
+  {
+    const size_t smem = 4 * 64 * PITCH + sizeof(float) * (128 + n_rel) + tb + 16;
+    auto kern = attn_mma_bwd_dq_kernel<HD, WINDOW>;
+    if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nq_pad / 64, Pn, P.H);
+    kern<<<grid, 128, smem, st>>>(P, delta, nq_pad, nk_pad);
+    if (check_launch("attn_mma_bwd_dq_kernel")) return 1;
+  }
+  {
+    const size_t smem = 4 * 64 * PITCH + sizeof(float) * 2 * nq_pad + tb + 16;
+    auto kern = attn_mma_bwd_dkv_kernel<HD, WINDOW>;
+    if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nk_pad / 64, Pn, P.H);
+    kern<<<grid, 128, smem, st>>>(P, delta, nq_pad, nk_pad);
+    return check_launch("attn_mma_bwd_dkv_kernel");
+  }
 }
 
 bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
@@ -533,16 +595,17 @@ int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V,
 }
 
 int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
-                long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, void* dQ, long long lddq,
-                float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq, float scale,
-                cudaStream_t st) {
+                long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta, void* dQ,
+                long long lddq, float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq,
+                float scale, cudaStream_t st) {
   AttnParams P = {};
   P.Q = (const bf16*)Q; P.K = (const bf16*)K; P.V = (const bf16*)V; P.ldq = ldq; P.ldk = ldk; P.ldv = ldv;
   P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.H = H; P.hd = hd; P.Nq = Nq; P.max_nk = ix.max_nk; P.scale = scale;
   P.dO = (const bf16*)dO; P.dQ = (bf16*)dQ; P.lddq = lddq; P.dK = dK; P.dV = dV; P.lddk = lddk; P.lddv = lddv;
   P.mha = ix;
-  VALOR_REQUIRE(H <= 65535, "mha: too many heads");
-  return hd == 32 ? launch_bwd<32, false>(P, Pn, Nq, ix.max_nk, st) : launch_bwd<64, false>(P, Pn, Nq, ix.max_nk, st);
+  VALOR_REQUIRE(Pn <= 65535 && H <= 65535, "mha: too many problems/heads");
+  return hd == 32 ? launch_bwd<32, false>(P, delta, Pn, Nq, ix.max_nk, st)
+                  : launch_bwd<64, false>(P, delta, Pn, Nq, ix.max_nk, st);
 }
 
 int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
@@ -557,8 +620,8 @@ int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O
 }
 
 int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
-                   const float* lse, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd, float scale,
-                   cudaStream_t st) {
+                   const float* lse, float* delta, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd,
+                   float scale, cudaStream_t st) {
   const int C = H * hd;
   AttnParams P = {};
   P.Q = (const bf16*)qkv; P.K = P.Q + C; P.V = P.Q + 2 * C; P.ldq = P.ldk = P.ldv = ld;
@@ -567,8 +630,8 @@ int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const v
   P.dK_lp = (bf16*)dqkv + C; P.dV_lp = (bf16*)dqkv + 2 * C; P.lddkv_lp = lddq;
   P.dtable = dtable;
   P.win = ix;
-  VALOR_REQUIRE(H <= 65535, "window_attn: too many heads");
-  return hd == 32 ? launch_bwd<32, true>(P, Pn, ix.N, ix.N, st) : launch_bwd<64, true>(P, Pn, ix.N, ix.N, st);
+  VALOR_REQUIRE(Pn <= 65535 && H <= 65535, "window_attn: too many windows/heads");
+  return hd == 32 ? launch_bwd<32, true>(P, delta, Pn, ix.N, ix.N, st) : launch_bwd<64, true>(P, delta, Pn, ix.N, ix.N, st);
 }
 
 }  // namespace valor

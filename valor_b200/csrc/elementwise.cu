@@ -333,30 +333,56 @@ int mean_pool_bwd(int dtype, const void* dy, void* dx, long long R, int X, int C
 // ---------------------------------------------------------------------------------------
 // bias gradient: db[n] += sum_m dy[m, n]   (dy row-major, pitch ld)
 // ---------------------------------------------------------------------------------------
+// Each warp reads 4 consecutive columns per lane (8-byte bf16 / 16-byte fp32 vectors): a CTA covers a
+// 128-column panel and a row range; partial sums meet in shared memory, one atomicAdd per column.
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ dy, long long ld, float* __restrict__ db, long long M, int N, int rows_per_block) {
-  __shared__ float sh[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + tx;
+  __shared__ float sh[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 128 + lane * 4;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  float s = 0.f;
-  if (col < N)
-    for (long long r = r0 + ty; r < r1; r += 8) s += to_f(dy[r * ld + col]);
-  sh[ty][tx] = s;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const bool vec = (c0 + 4 <= N) && (ld % 4 == 0) && ((((uintptr_t)dy) & 15) == 0);
+  if (vec) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      float f[4];
+      if (sizeof(T) == 2) {
+        const uint2 v = *(const uint2*)((const bf16*)dy + r * ld + c0);
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&v;
+        const float2 x = __bfloat1622float2(h[0]), y = __bfloat1622float2(h[1]);
+        f[0] = x.x; f[1] = x.y; f[2] = y.x; f[3] = y.y;
+      } else {
+        const float4 v = *(const float4*)((const float*)dy + r * ld + c0);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+      }
+      a0 += f[0]; a1 += f[1]; a2 += f[2]; a3 += f[3];
+    }
+  } else {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      if (c0 + 0 < N) a0 += to_f(dy[r * ld + c0 + 0]);
+      if (c0 + 1 < N) a1 += to_f(dy[r * ld + c0 + 1]);
+      if (c0 + 2 < N) a2 += to_f(dy[r * ld + c0 + 2]);
+      if (c0 + 3 < N) a3 += to_f(dy[r * ld + c0 + 3]);
+    }
+  }
+  sh[warp][lane * 4 + 0] = a0; sh[warp][lane * 4 + 1] = a1; sh[warp][lane * 4 + 2] = a2; sh[warp][lane * 4 + 3] = a3;
   __syncthreads();
-  if (ty == 0 && col < N) {
-    float t = 0.f;
+  if (threadIdx.x < 128) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col < N) {
+      float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][tx];
-    atomicAdd(&db[col], t);
+      for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+      atomicAdd(&db[col], t);
+    }
   }
 }
 int colsum(int dtype, const void* dy, long long ld, float* db, long long M, int N, cudaStream_t st) {
   if (M == 0) return 0;
-  const int cb = (N + 31) / 32;
+  const int cb = (N + 127) / 128;
   long long want_rb = ((long long)num_sms() * 8 + cb - 1) / cb;
   long long rows_per_block = (M + want_rb - 1) / want_rb;
   if (rows_per_block < 64) rows_per_block = 64;

@@ -96,29 +96,33 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGING_BYTES = 4 * 16384;  // per epilogue half: 128x64 bf16 out tile + pre-activation tile
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - BLOCK_N * 4 /*bias*/ - STAGING_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BLOCK_N * 4;
 };
 
 template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                   void* __restrict__ Cptr, long long ldc, int M, int N, int K, int k_splits, int vec_ok,
-                  GemmEpilogue ep) {
+                  int tma_store, GemmEpilogue ep) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 8 KB)
+  uint64_t* bars = (uint64_t*)(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
-  float* bias_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  float* bias_s = (float*)(staging + Cfg::STAGING_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,7 +144,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -231,9 +235,16 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may touch
-    const int et = threadIdx.x - 128;
+    // ===================== epilogue (8 warps) =====================
+    // warp e: TMEM lane quarter q = e % 4 (hardware restriction: warp_id % 4), column half = e / 4.
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int half = e >> 2;
+    const int et = threadIdx.x - 128;           // 0..255
+    const int r_tile = q * 32 + lane;           // row inside the 128-row tile
+    const bool issuer = (q == 0 && lane == 0);  // one thread per half drives the TMA stores
+    uint8_t* st_out = staging + half * 32768;
+    uint8_t* st_pre = st_out + 16384;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -242,112 +253,168 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m_blk = rest / k_splits;
       const int ks = rest % k_splits;
       const int n0 = n_blk * BLOCK_N;
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row = m_blk * BLOCK_M + r_tile;
       // stage the bias slice (only split 0 adds bias when split-K accumulates)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < BLOCK_N; i += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < BLOCK_N; i += 256) {
         float b = 0.f;
         if (ep.bias != nullptr && ks == 0 && n0 + i < N) b = ep.bias[n0 + i];
         bias_s[i] = b;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
+      if (tma_store) {
+        // ---------- bf16 output through swizzled smem staging + TMA store (coalesced, OOB-clipped) ----------
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < M && col0 < N) {
-          float x[32];
+        for (int c = half; c < BLOCK_N / 64; c += 2) {
+          if (n0 + c * 64 >= N) break;
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+          else asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 32 + j];
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 64 + sub * 32, v);
+            tmem_ld_wait();
+            const int col0 = n0 + c * 64 + sub * 32;
+            float x[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= N) break;
-            float* xg = x + g * 8;
-            const bool full = vec_ok && (col + 8 <= N);
-            const int nvalid = (N - col) < 8 ? (N - col) : 8;
-            // ---- pre-activation side output
-            if (ep.preact_out != nullptr) {
-              bf16* dst = (bf16*)ep.preact_out + (size_t)row * ep.ld_pre + col;
-              if (full) {
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 64 + sub * 32 + j];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              float* xg = x + g * 8;
+              const int chunk = sub * 4 + g;  // 16-byte chunk inside the 128-byte staging row
+              const uint32_t soff = (uint32_t)r_tile * 128u + (uint32_t)((chunk ^ (r_tile & 7)) << 4);
+              if (ep.preact_out != nullptr) {
                 uint4 pk;
                 __nv_bfloat162* h = (__nv_bfloat162*)&pk;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
-                *(uint4*)dst = pk;
-              } else {
+                *(uint4*)(st_pre + soff) = pk;
+              }
+              const bool inb = row < M && col + 8 <= N;
+              if (ep.act_aux != nullptr) {
+                if (inb) {
+                  uint4 a = *(const uint4*)((const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col);
+                  const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = __bfloat1622float2(h[j]);
+                    xg[2 * j] *= act_grad(f.x, ep.act);
+                    xg[2 * j + 1] *= act_grad(f.y, ep.act);
+                  }
+                } else if (row < M) {
+                  for (int j = 0; j < 8 && col + j < N; ++j)
+                    xg[j] *= act_grad(__bfloat162float(((const bf16*)ep.act_aux)[(size_t)row * ep.ld_aux + col + j]), ep.act);
+                }
+              } else if (ep.act != VALOR_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
+              }
+              if (ep.residual != nullptr) {
+                if (inb) {
+                  uint4 r = *(const uint4*)((const bf16*)ep.residual + (size_t)row * ep.ldr + col);
+                  const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = __bfloat1622float2(h[j]);
+                    xg[2 * j] += f.x;
+                    xg[2 * j + 1] += f.y;
+                  }
+                } else if (row < M) {
+                  for (int j = 0; j < 8 && col + j < N; ++j)
+                    xg[j] += __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col + j]);
+                }
+              }
+              uint4 pk;
+              __nv_bfloat162* h = (__nv_bfloat162*)&pk;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
+              *(uint4*)(st_out + soff) = pk;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+          else asm volatile("bar.sync 3, 128;" ::: "memory");
+          if (issuer) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             (uint64_t)&tmC),
+                         "r"(smem_u32(st_out)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M)
+                         : "memory");
+            if (ep.preact_out != nullptr)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               (uint64_t)&tmP),
+                           "r"(smem_u32(st_pre)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
+        // ---------- direct stores (fp32 / split-K accumulate / unaligned outputs) ----------
+#pragma unroll 1
+        for (int c = half; c < BLOCK_N / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row < M && col0 < N) {
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 32 + j];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col >= N) break;
+              float* xg = x + g * 8;
+              const bool full = vec_ok && (col + 8 <= N);
+              const int nvalid = (N - col) < 8 ? (N - col) : 8;
+              if (ep.preact_out != nullptr) {
+                bf16* dst = (bf16*)ep.preact_out + (size_t)row * ep.ld_pre + col;
                 for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(xg[j]);
               }
-            }
-            // ---- activation or activation gradient
-            if (ep.act_aux != nullptr) {
-              const bf16* src = (const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col;
-              if (full) {
-                uint4 a = *(const uint4*)src;
-                const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 f = __bfloat1622float2(h[j]);
-                  xg[2 * j] *= act_grad(f.x, ep.act);
-                  xg[2 * j + 1] *= act_grad(f.y, ep.act);
-                }
-              } else {
+              if (ep.act_aux != nullptr) {
+                const bf16* src = (const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col;
                 for (int j = 0; j < nvalid; ++j) xg[j] *= act_grad(__bfloat162float(src[j]), ep.act);
+              } else if (ep.act != VALOR_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
               }
-            } else if (ep.act != VALOR_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
-            }
-            // ---- residual
-            if (ep.residual != nullptr) {
-              const bf16* src = (const bf16*)ep.residual + (size_t)row * ep.ldr + col;
-              if (full) {
-                uint4 r = *(const uint4*)src;
-                const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 f = __bfloat1622float2(h[j]);
-                  xg[2 * j] += f.x;
-                  xg[2 * j + 1] += f.y;
-                }
-              } else {
+              if (ep.residual != nullptr) {
+                const bf16* src = (const bf16*)ep.residual + (size_t)row * ep.ldr + col;
                 for (int j = 0; j < nvalid; ++j) xg[j] += __bfloat162float(src[j]);
               }
-            }
-            // ---- store
-            if (ep.out_dtype == VALOR_DT_BF16) {
-              bf16* dst = (bf16*)Cptr + (size_t)row * ldc + col;
-              if (full) {
-                uint4 pk;
-                __nv_bfloat162* h = (__nv_bfloat162*)&pk;
+              if (ep.out_dtype == VALOR_DT_BF16) {
+                bf16* dst = (bf16*)Cptr + (size_t)row * ldc + col;
+                if (full) {
+                  uint4 pk;
+                  __nv_bfloat162* h = (__nv_bfloat162*)&pk;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
-                *(uint4*)dst = pk;
-              } else {
-                for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(xg[j]);
-              }
-            } else {
-              float* dst = (float*)Cptr + (size_t)row * ldc + col;
-              if (full && (ldc % 4 == 0)) {
-                if (ep.accumulate) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xg[0]), "f"(xg[1]),
-                               "f"(xg[2]), "f"(xg[3])
-                               : "memory");
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(xg[4]), "f"(xg[5]),
-                               "f"(xg[6]), "f"(xg[7])
-                               : "memory");
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
+                  *(uint4*)dst = pk;
                 } else {
-                  *(float4*)dst = make_float4(xg[0], xg[1], xg[2], xg[3]);
-                  *(float4*)(dst + 4) = make_float4(xg[4], xg[5], xg[6], xg[7]);
+                  for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(xg[j]);
                 }
               } else {
-                for (int j = 0; j < nvalid; ++j) {
-                  if (ep.accumulate) atomicAdd(dst + j, xg[j]);
-                  else dst[j] = xg[j];
+                float* dst = (float*)Cptr + (size_t)row * ldc + col;
+                if (full && (ldc % 4 == 0)) {
+                  if (ep.accumulate) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xg[0]), "f"(xg[1]),
+                                 "f"(xg[2]), "f"(xg[3])
+                                 : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(xg[4]),
+                                 "f"(xg[5]), "f"(xg[6]), "f"(xg[7])
+                                 : "memory");
+                  } else {
+                    *(float4*)dst = make_float4(xg[0], xg[1], xg[2], xg[3]);
+                    *(float4*)(dst + 4) = make_float4(xg[4], xg[5], xg[6], xg[7]);
+                  }
+                } else {
+                  for (int j = 0; j < nvalid; ++j) {
+                    if (ep.accumulate) atomicAdd(dst + j, xg[j]);
+                    else dst[j] = xg[j];
+                  }
                 }
               }
             }
@@ -359,6 +426,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (tma_store && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -386,6 +454,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D bf16 tensor, `inner` contiguous, row pitch `ld` elements; box = {64, box_outer}, 128B swizzle.
 static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  memset(tm, 0, sizeof(*tm));
   auto fn = get_encode_fn();
   VALOR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {inner, outer};
@@ -401,8 +470,9 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
 }
 
 template <int BN, bool AK, bool BK>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, void* C, long long ldc, int M, int N, int K,
-                      int k_splits, int vec_ok, const GemmEpilogue& ep, int grid, cudaStream_t st) {
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, void* C,
+                      long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
+                      const GemmEpilogue& ep, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_sm100_kernel<BN, AK, BK>;
   static bool attr_done = false;
@@ -410,18 +480,19 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, void* C, lon
     VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep);
   return check_launch("gemm_sm100_kernel");
 }
 
 template <bool AK, bool BK>
-static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, long long ldc, int M, int N, int K,
-                     int k_splits, int vec_ok, const GemmEpilogue& ep, int grid, cudaStream_t st) {
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+                     void* C, long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
+                     const GemmEpilogue& ep, int grid, cudaStream_t st) {
   switch (bn) {
-    case 64: return launch_cfg<64, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
-    case 128: return launch_cfg<128, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
-    case 192: return launch_cfg<192, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
-    default: return launch_cfg<256, AK, BK>(ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+    case 64: return launch_cfg<64, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    case 128: return launch_cfg<128, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    case 192: return launch_cfg<192, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    default: return launch_cfg<256, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
   }
 }
 
@@ -488,12 +559,24 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   if (ep.act_aux) vec_ok = vec_ok && (ep.ld_aux % 8 == 0) && (((uintptr_t)ep.act_aux & 15) == 0);
   if (ep.preact_out) vec_ok = vec_ok && (ep.ld_pre % 8 == 0) && (((uintptr_t)ep.preact_out & 15) == 0);
 
+  // bf16 outputs with 16-byte aligned pitches leave through swizzled smem staging + TMA store
+  int tma_store = (ep.out_dtype == VALOR_DT_BF16) && (ldc % 8 == 0) && (((uintptr_t)C & 15) == 0) && !ep.accumulate;
+  if (ep.preact_out) tma_store = tma_store && (ep.ld_pre % 8 == 0) && (((uintptr_t)ep.preact_out & 15) == 0);
+  if (ep.residual) tma_store = tma_store && (ep.ldr % 8 == 0) && (((uintptr_t)ep.residual & 15) == 0);
+  if (ep.act_aux) tma_store = tma_store && (ep.ld_aux % 8 == 0) && (((uintptr_t)ep.act_aux & 15) == 0);
+  CUtensorMap tc, tp;
+  memset(&tc, 0, sizeof(tc));
+  memset(&tp, 0, sizeof(tp));
+  if (tma_store) {
+    if (make_tmap(&tc, C, N, M, ldc, BLOCK_M)) return 1;
+    if (ep.preact_out && make_tmap(&tp, ep.preact_out, N, M, ep.ld_pre, BLOCK_M)) return 1;
+  }
   const long total = (long)m_blocks * n_blocks * k_splits;
   const int grid = (int)(total < sms ? total : sms);
-  if (a_kmajor && b_kmajor) return launch_bn<true, true>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
-  if (a_kmajor && !b_kmajor) return launch_bn<true, false>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
-  if (!a_kmajor && b_kmajor) return launch_bn<false, true>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
-  return launch_bn<false, false>(bn, ta, tb, C, ldc, M, N, K, k_splits, vec_ok, ep, grid, st);
+  if (a_kmajor && b_kmajor) return launch_bn<true, true>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+  if (a_kmajor && !b_kmajor) return launch_bn<true, false>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+  if (!a_kmajor && b_kmajor) return launch_bn<false, true>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+  return launch_bn<false, false>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
 }
 
 }  // namespace valor

@@ -82,8 +82,8 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
 template <typename T, int VPL /* float4-groups per lane; N == VPL*128 */>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int N) {
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ dres,
+                     T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int N) {
   extern __shared__ float sh[];  // [2][N]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
@@ -124,6 +124,12 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = (fdy[k][e] - s1 - fxh[k][e] * s2) * rs;
+      if (dres != nullptr) {  // gradient arriving through the residual branch that bypasses this LN
+        Vec4<T> rv; rv.load(dres + row * N + c);
+        float rf[4]; rv.get(rf);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] += rf[e];
+      }
       Vec4<T> v; v.set(o); v.store(dx + row * N + c);
     }
   }
@@ -147,8 +153,9 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_generic_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
-                             const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-                             float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int N) {
+                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                             const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma,
+                             float* __restrict__ dbeta, long long M, int N) {
   extern __shared__ float sh[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
@@ -169,7 +176,9 @@ layernorm_bwd_generic_kernel(const T* __restrict__ dy, const T* __restrict__ x, 
     s2 = warp_sum(s2) / N;
     for (int c = lane; c < N; c += 32) {
       const float d = to_f(dyr[c]) * gamma[c], xh = (to_f(xr[c]) - mu) * rs;
-      dx[row * N + c] = from_f<T>((d - s1 - xh * s2) * rs);
+      float o = (d - s1 - xh * s2) * rs;
+      if (dres != nullptr) o += to_f(dres[row * N + c]);
+      dx[row * N + c] = from_f<T>(o);
     }
   }
   __syncthreads();
@@ -181,21 +190,21 @@ layernorm_bwd_generic_kernel(const T* __restrict__ dy, const T* __restrict__ x, 
 
 template <typename T>
 static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                           void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
+                           const void* dres, void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
   long long want = (M + 7) / 8;
   int grid = (int)(want < (long long)num_sms() * 4 ? want : (long long)num_sms() * 4);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * N * sizeof(float);
 #define LN_BWD_CASE(V)                                                                                          \
   case V * 128:                                                                                                 \
-    layernorm_bwd_kernel<T, V><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,   \
-                                                         dgamma, dbeta, M, N);                                  \
+    layernorm_bwd_kernel<T, V><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,           \
+                                                         (const T*)dres, (T*)dx, dgamma, dbeta, M, N);          \
     break;
   switch (N) {
     LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(4) LN_BWD_CASE(6) LN_BWD_CASE(8) LN_BWD_CASE(16)
     default:
-      layernorm_bwd_generic_kernel<T><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx,
-                                                                dgamma, dbeta, M, N);
+      layernorm_bwd_generic_kernel<T><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,
+                                                                (const T*)dres, (T*)dx, dgamma, dbeta, M, N);
   }
 #undef LN_BWD_CASE
   return check_launch("layernorm_bwd_kernel");
@@ -215,11 +224,11 @@ int layernorm_fwd(int dtype, const void* x, const float* gamma, const float* bet
 }
 
 int layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                  void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
+                  const void* dres, void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
   VALOR_REQUIRE(N % 4 == 0, "layernorm: N=%d must be a multiple of 4", N);
   if (M == 0) return 0;
-  if (dtype == VALOR_DT_F32) return ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, N, st);
-  return ln_bwd_dispatch<bf16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, M, N, st);
+  if (dtype == VALOR_DT_F32) return ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, M, N, st);
+  return ln_bwd_dispatch<bf16>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, M, N, st);
 }
 
 // ---------------------------------------------------------------------------------------

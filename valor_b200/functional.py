@@ -150,6 +150,30 @@ def layer_norm(x, ln):
     return LayerNormFn.apply(x, ln)
 
 
+class LayerNormResidualFn(Function):
+    """(y, x_res) = (LN(x), x): the pre-norm pattern x + f(LN(x)).  `x_res` feeds the residual add of the
+    branch's last GEMM; in the backward the gradient of that residual path is added inside the LN-backward
+    kernel (one pass) instead of a separate elementwise accumulation of two full [tokens, C] tensors."""
+
+    @staticmethod
+    def forward(ctx, x, ln):
+        x = x.contiguous()
+        y, mean, rstd = K.layernorm_fwd(x, ln.g, ln.b, ln.eps)
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.ln = ln
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, mean, rstd = ctx.saved_tensors
+        ln = ctx.ln
+        return K.layernorm_bwd(dy, x, ln.g, mean, rstd, ln.g_grad, ln.b_grad, dres=dres), None
+
+
+def layer_norm_residual(x, ln):
+    return LayerNormResidualFn.apply(x, ln)
+
+
 class WindowAttnFn(Function):
     """WindowAttention3D core on the natural token order (see include/valor_b200.h)."""
 

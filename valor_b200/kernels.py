@@ -96,11 +96,14 @@ def layernorm_fwd(x, gamma, beta, eps):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
     M, N = x.shape
     dy = dy.contiguous()
     dx = torch.empty_like(x)
-    _call("valor_layernorm_bwd", DT(x), P(dy), P(x), P(gamma), P(mean), P(rstd), P(dx), P(dgamma), P(dbeta), M, N, ST())
+    if dres is not None:
+        dres = dres.contiguous()
+    _call("valor_layernorm_bwd", DT(x), P(dy), P(x), P(gamma), P(mean), P(rstd), P(dres), P(dx), P(dgamma), P(dbeta),
+          M, N, ST())
     return dx
 
 
@@ -138,7 +141,8 @@ def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=No
     dkv = torch.zeros(k.shape[0], 2 * H * hd, device=q.device, dtype=torch.float32)
     dk, dv = dkv[:, : H * hd], dkv[:, H * hd:]
     do = do.contiguous()
-    _call("valor_mha_bwd", DT(q), P(q), P(k), P(v), P(o), P(do), _ld(q), _ld(k), _ld(v), _ld(o), P(lse), P(dq_out),
+    delta = torch.empty_like(lse)
+    _call("valor_mha_bwd", DT(q), P(q), P(k), P(v), P(o), P(do), _ld(q), _ld(k), _ld(v), _ld(o), P(lse), P(delta), P(dq_out),
           _ld(dq_out), P(dk), P(dv), _ld(dk), _ld(dv), P_, H, hd, Nq, max_nk, P(q_row0), P(kv_row0), P(kv_len),
           P(key_valid), P(causal), float(scale), backend, ST())
     return dkv
@@ -162,7 +166,8 @@ def window_attn_bwd(qkv, o, do, lse, table, dtable, grid, win, shift, cfg_win, h
     do = do.contiguous()
     nbytes = _lib.load().valor_window_attn_bwd_scratch_bytes(DT(qkv), qkv.shape[0], heads, hd, _ld(qkv), backend)
     scratch = torch.zeros(nbytes // 4, device=qkv.device, dtype=torch.float32) if nbytes else None
-    _call("valor_window_attn_bwd", DT(qkv), P(qkv), _ld(qkv), P(o), P(do), _ld(o), P(lse), P(table), P(dqkv),
+    delta = torch.empty_like(lse)
+    _call("valor_window_attn_bwd", DT(qkv), P(qkv), _ld(qkv), P(o), P(do), _ld(o), P(lse), P(delta), P(table), P(dqkv),
           _ld(dqkv), P(scratch), P(dtable), B, D, H, W, *win, *shift, *cfg_win, heads, hd, float(scale), backend, ST())
     return dqkv
 

@@ -43,15 +43,15 @@ class TransformerLayer(nn.Module):
         att = self.attention
         H = att.head_num
         hd = att.hidden_size // H
-        h = Fn.layer_norm(x, LN(self.layernorm1.weight, self.layernorm1.bias, 1e-12))
+        h, xr = Fn.layer_norm_residual(x, LN(self.layernorm1.weight, self.layernorm1.bias, 1e-12))
         qkv = Fn.linear(h, fused_lin([l.weight for l in att.linears[:3]], [l.bias for l in att.linears[:3]]))
         spec = dict(P=n_seq, H=H, hd=hd, Nq=seq_len, max_nk=seq_len, scale=1.0 / math.sqrt(hd))
         o = Fn.SelfAttnFn.apply(qkv, spec)
-        x = Fn.linear(o, lin_of(att.linears[3].weight, att.linears[3].bias), residual=x)
-        h = Fn.layer_norm(x, LN(self.layernorm2.weight, self.layernorm2.bias, 1e-12))
+        x = Fn.linear(o, lin_of(att.linears[3].weight, att.linears[3].bias), residual=xr)
+        h, xr = Fn.layer_norm_residual(x, LN(self.layernorm2.weight, self.layernorm2.bias, 1e-12))
         ff = self.ff_layer
         return Fn.mlp(h, lin_of(ff.linear1.weight, ff.linear1.bias), lin_of(ff.linear2.weight, ff.linear2.bias),
-                      K.ACT_GELU, residual=x)
+                      K.ACT_GELU, residual=xr)
 
 
 class TransformerEncoder(nn.Module):
