@@ -255,6 +255,39 @@ def main():
         train_step(resident)
         torch.cuda.synchronize()
         log(f"eager warmup step {i} done")
+    # ---- roofline pass: CUDA events around every GEMM launch of one more step (outside the timed region)
+    roof = None
+    peak_tf, peak_hbm, peak_kind = peaks()
+    if not args.no_roofline and rank == 0:
+        recs = []
+        orig = K.gemm
+
+        def gemm_probe(a, b, **kw):
+            M, Kd = (a.shape if kw.get("a_kmajor", True) else (a.shape[1], a.shape[0]))
+            N = b.shape[0] if kw.get("b_kmajor", True) else b.shape[1]
+            tensor = a.dtype == torch.bfloat16 and N >= 8 and Kd >= 8 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(a, b, **kw)
+            e.record()
+            recs.append((2.0 * M * N * Kd, s, e, tensor))
+            return r
+
+        K.gemm = gemm_probe
+        try:
+            train_step(resident)
+            torch.cuda.synchronize()
+        finally:
+            K.gemm = orig
+        t_ms = sum(s.elapsed_time(e) for f, s, e, t in recs if t)
+        fl = sum(f for f, s, e, t in recs if t)
+        n_t = sum(1 for r in recs if r[3])
+        ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_kind": f"{peak_kind} (sustained bf16)",
+                "launches_per_step": n_t, "gemm_ms_per_step": t_ms, "gemm_tflop_per_step": fl / 1e12,
+                "gemm_share_of_step": None}
+
     # ---- capture the whole step (forward, backward, all-reduce, clip, AdamW) in one CUDA graph: the C ABI
     # never syncs or allocates, so ~2000 launches replay without Python / launch latency
     graph = None
@@ -321,39 +354,6 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     log(f"e2e: {ms_e2e:.2f} ms/step")
 
-    # ---- roofline pass: CUDA events around every GEMM launch of one more step (outside the timed region)
-    roof = None
-    peak_tf, peak_hbm, peak_kind = peaks()
-    if not args.no_roofline and rank == 0:
-        recs = []
-        orig = K.gemm
-
-        def gemm_probe(a, b, **kw):
-            M, Kd = (a.shape if kw.get("a_kmajor", True) else (a.shape[1], a.shape[0]))
-            N = b.shape[0] if kw.get("b_kmajor", True) else b.shape[1]
-            tensor = a.dtype == torch.bfloat16 and N >= 8 and Kd >= 8 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig(a, b, **kw)
-            e.record()
-            recs.append((2.0 * M * N * Kd, s, e, tensor))
-            return r
-
-        K.gemm = gemm_probe
-        try:
-            eager_step(resident)
-            torch.cuda.synchronize()
-        finally:
-            K.gemm = orig
-        t_ms = sum(s.elapsed_time(e) for f, s, e, t in recs if t)
-        fl = sum(f for f, s, e, t in recs if t)
-        n_t = sum(1 for r in recs if r[3])
-        ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_kind": f"{peak_kind} (sustained bf16)",
-                "launches_per_step": n_t, "gemm_ms_per_step": t_ms, "gemm_tflop_per_step": fl / 1e12,
-                "gemm_share_of_step": t_ms / ms_step}
-
     value = world * B / (ms_step * 1e-3)
     e2e_val = world * B / (ms_e2e * 1e-3)
     line = {"metric": "pretrain samples/sec (video+audio+text)", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -369,6 +369,7 @@ def main():
             "gpu_launches": launches, "cuda_graph": graph is not None, "clocks": clocks, "losses": loss_vals,
             "step_mfu": FLOPS_PER_SAMPLE * B / (ms_step * 1e-3) / (peak_tf * 1e12) if args.geom == "base" else None}
     if roof:
+        roof["gemm_share_of_step"] = roof["gemm_ms_per_step"] / ms_step
         line["roofline"] = roof
     log("roofline pass done")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -35,31 +35,49 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *(uint32_t*)&v;
 }
 
+// explicit shared-space loads: the per-problem tables are reached through 32-bit shared addresses so the
+// compiler emits LDS (a generic pointer kept in a struct degrades every table access to a generic LD)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_v2u32(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_v2f32(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 static constexpr int BQ = 64, BKEY = 64;
 static constexpr float LOG2E = 1.4426950408889634f;
 static constexpr float LN2 = 0.6931471805599453f;
 
 // ---- per-problem tables in shared memory -------------------------------------------------
+// One 32-bit info word per token keeps the per-element work short:
+//   window : bits[0,16) relative-position code (query words carry code + center), bits[16,24) mask region
+//   mha    : bit0 = key is padding (-10000)
+//   both   : bit31 = key beyond the problem's key count (-inf, only the ragged last block)
 struct Tables {
   int* qrow;            // [NqPad] global row of query i (-1 = padding)
   int* krow;            // [NkPad]
-  short* code;          // window: relative-position code per local token
-  unsigned char* reg;   // window: mask region per local token
-  unsigned char* kval;  // mha: key validity
-  float* tab;           // window: this head's column of the bias table
-  int center, causal, nq, nk;
+  uint32_t* qinfo;      // [NqPad]
+  uint32_t* kinfo;      // [NkPad]
+  float* tab2;          // window: this head's column of the bias table, pre-multiplied by log2(e)
+  uint32_t qrow_s, krow_s, qinfo_s, kinfo_s, tab2_s;  // the same arrays as 32-bit shared addresses
+  int causal, nq, nk, shifted;
 };
 
+static constexpr float M100_2 = -100.0f * 1.4426950408889634f;      // videoswin.py:284, log2 domain
+static constexpr float M10000_2 = -10000.0f * 1.4426950408889634f;  // bert.py:885, log2 domain
+
+// score in the log2 domain: s*scale*log2e + bias/mask
 template <bool WINDOW>
-__device__ __forceinline__ float add_term(const Tables& t, int i, int j) {
+__device__ __forceinline__ float score2(const Tables& t, float s, float sc2, uint32_t qi, uint32_t kj, int i, int j) {
+  float v;
   if (WINDOW) {
-    float a = t.tab[t.code[i] - t.code[j] + t.center];
-    if (t.reg[i] != t.reg[j]) a += -100.0f;
-    return a;
+    v = fmaf(s, sc2, lds_f32(t.tab2_s + 4u * (uint32_t)((int)(qi & 0xffffu) - (int)(kj & 0xffffu))));
+    if (t.shifted && ((qi ^ kj) & 0x00ff0000u)) v += M100_2;
   } else {
-    const bool masked = (t.kval != nullptr && t.kval[j] == 0) || (t.causal && j > i);
-    return masked ? -10000.0f : 0.0f;
+    v = s * sc2;
+    if ((kj & 1u) || (t.causal && j > i)) v += M10000_2;
   }
+  return v;
 }
 
 struct AttnParams {
@@ -81,84 +99,124 @@ struct AttnParams {
 };
 
 template <bool WINDOW>
-__device__ void build_tables(Tables& t, unsigned char* base, const AttnParams& P, int p, int h, int nq_pad, int nk_pad) {
-  // carve
+__device__ __forceinline__ void build_tables(Tables& t, unsigned char* base, const AttnParams& P, int p, int h, int nq_pad, int nk_pad) {
   t.qrow = (int*)base; base += sizeof(int) * nq_pad;
+  t.qinfo = (uint32_t*)base; base += sizeof(uint32_t) * nq_pad;
   if (WINDOW) {
-    t.krow = t.qrow;
-    t.code = (short*)base; base += sizeof(short) * nq_pad;
-    t.reg = base; base += (nq_pad + 15) / 16 * 16;
-    t.kval = nullptr;
-    t.tab = (float*)base;
+    t.kinfo = (uint32_t*)base; base += sizeof(uint32_t) * nq_pad;
+    t.krow = (int*)base; base += sizeof(int) * nq_pad;
+    t.tab2 = (float*)base;
     const WindowIndex& ix = P.win;
     t.nq = t.nk = ix.N;
     t.causal = 0;
+    t.shifted = (ix.sd | ix.sh | ix.sw) != 0;
     const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
-    t.center = (ix.WD - 1) * cH + (ix.WH - 1) * cW + (ix.WW - 1);
+    const int center = (ix.WD - 1) * cH + (ix.WH - 1) * cW + (ix.WW - 1);
+    // Queries keep the natural (d,h,w) order.  KEYS are enumerated (w,d,h) with h fastest: softmax does not
+    // care about key order, and consecutive keys then differ by 13 in relative-position code while consecutive
+    // queries differ by 1, so the 32 lanes of an MMA fragment hit 32 distinct bias-table slots (conflict-free
+    // shared-memory gradient atomics and table reads).
     for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {
       if (i < ix.N) {
         int cd, ch, cw, b;
-        ix.coords(p, i, cd, ch, cw, b);
-        t.qrow[i] = (int)ix.row(p, i);
-        const int ld = i / (ix.wh * ix.ww), lh = (i / ix.ww) % ix.wh, lw = i % ix.ww;
-        t.code[i] = (short)(ld * cH + lh * cW + lw);
-        t.reg[i] = (unsigned char)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
-                                   ix.region(cw, ix.W, ix.ww, ix.sw));
+        {
+          ix.coords(p, i, cd, ch, cw, b);
+          t.qrow[i] = (int)ix.row(p, i);
+          const int ld = i / (ix.wh * ix.ww), lh = (i / ix.ww) % ix.wh, lw = i % ix.ww;
+          const uint32_t code = (uint32_t)(ld * cH + lh * cW + lw);
+          const uint32_t reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
+                                          ix.region(cw, ix.W, ix.ww, ix.sw));
+          t.qinfo[i] = (code + (uint32_t)center) | (reg << 16);
+        }
+        {
+          const int lh = i % ix.wh, ld = (i / ix.wh) % ix.wd, lw = i / (ix.wh * ix.wd);
+          const int nat = (ld * ix.wh + lh) * ix.ww + lw;
+          ix.coords(p, nat, cd, ch, cw, b);
+          t.krow[i] = (int)ix.row(p, nat);
+          const uint32_t code = (uint32_t)(ld * cH + lh * cW + lw);
+          const uint32_t reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
+                                          ix.region(cw, ix.W, ix.ww, ix.sw));
+          t.kinfo[i] = code | (reg << 16);
+        }
       } else {
-        t.qrow[i] = -1; t.code[i] = 0; t.reg[i] = 0;
+        t.qrow[i] = -1; t.krow[i] = -1; t.kinfo[i] = 0x80000000u; t.qinfo[i] = (uint32_t)center;
       }
     }
     const int n_rel = (2 * ix.WD - 1) * cH;
-    for (int r = threadIdx.x; r < n_rel; r += blockDim.x) t.tab[r] = ix.table[(size_t)r * ix.heads + h];
+    for (int r = threadIdx.x; r < n_rel; r += blockDim.x) t.tab2[r] = ix.table[(size_t)r * ix.heads + h] * LOG2E;
   } else {
     t.krow = (int*)base; base += sizeof(int) * nk_pad;
-    t.kval = base;
-    t.code = nullptr; t.reg = nullptr; t.tab = nullptr; t.center = 0;
+    t.kinfo = (uint32_t*)base;
+    t.tab2 = nullptr;
+    t.shifted = 0;
     const MhaIndex& ix = P.mha;
     t.nq = ix.Nq;
     t.nk = ix.nk(p);
     t.causal = ix.causal ? (int)ix.causal[p] : 0;
-    for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) t.qrow[i] = i < t.nq ? (int)ix.qrow(p, i) : -1;
+    for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) { t.qrow[i] = i < t.nq ? (int)ix.qrow(p, i) : -1; t.qinfo[i] = 0; }
     for (int j = threadIdx.x; j < nk_pad; j += blockDim.x) {
       t.krow[j] = j < t.nk ? (int)ix.krow(p, j) : -1;
-      t.kval[j] = (j < t.nk && (ix.key_valid == nullptr || ix.key_valid[(size_t)p * ix.max_nk + j])) ? 1 : 0;
+      uint32_t w = 0;
+      if (j >= t.nk) w = 0x80000000u;
+      else if (ix.key_valid != nullptr && ix.key_valid[(size_t)p * ix.max_nk + j] == 0) w = 1u;
+      t.kinfo[j] = w;
     }
-    if (ix.key_valid == nullptr) t.kval = t.kval;  // all ones within nk; padding handled by nk bound
   }
+  t.qrow_s = s_u32(t.qrow); t.krow_s = s_u32(t.krow); t.qinfo_s = s_u32(t.qinfo); t.kinfo_s = s_u32(t.kinfo);
+  t.tab2_s = t.tab2 ? s_u32(t.tab2) : 0u;
 }
 
 // gather 64 rows x HD bf16 (16-byte chunks) into a padded smem tile; rows < 0 -> zeros
 template <int HD>
-__device__ __forceinline__ void load_tile(unsigned char* dst, const bf16* src, long long ld, int col0, const int* rows, int r0) {
+__device__ __forceinline__ void load_tile(unsigned char* dst, const bf16* src, long long ld, int col0, uint32_t rows_s, int r0) {
   constexpr int PITCH = HD * 2 + 16, CH = HD / 8;
   for (int c = threadIdx.x; c < 64 * CH; c += blockDim.x) {
     const int r = c / CH, ch = c % CH;
-    const int gr = rows[r0 + r];
+    const int gr = lds_s32(rows_s + 4u * (uint32_t)(r0 + r));
     uint4 v = make_uint4(0, 0, 0, 0);
     if (gr >= 0) v = *(const uint4*)(src + (size_t)gr * ld + col0 + ch * 8);
     *(uint4*)(dst + r * PITCH + ch * 16) = v;
   }
 }
 
+// same gather, issued as cp.async (16-byte, zero-fill for padding rows): the copy of block i+1 overlaps
+// the MMA / softmax work on block i
+template <int HD>
+__device__ __forceinline__ void load_tile_async(unsigned char* dst, const bf16* src, long long ld, int col0, uint32_t rows_s, int r0) {
+  constexpr int PITCH = HD * 2 + 16, CH = HD / 8;
+  for (int c = threadIdx.x; c < 64 * CH; c += blockDim.x) {
+    const int r = c / CH, ch = c % CH;
+    const int gr = lds_s32(rows_s + 4u * (uint32_t)(r0 + r));
+    const bf16* g = src + (size_t)(gr < 0 ? 0 : gr) * ld + col0 + ch * 8;
+    const uint32_t d = s_u32(dst + r * PITCH + ch * 16);
+    const int nbytes = gr < 0 ? 0 : 16;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(nbytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ==========================================================================================
 // forward: grid (ceil(Nq/64), P, H), 128 threads; warp w owns query rows [w*16, w*16+16)
 // ==========================================================================================
 template <int HD, bool WINDOW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
-  constexpr int PITCH = HD * 2 + 16;
+  constexpr int PITCH = HD * 2 + 16, TILE = 64 * PITCH;
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* Qs = smem;
-  unsigned char* Ks = Qs + 64 * PITCH;
-  unsigned char* Vs = Ks + 64 * PITCH;
-  __shared__ Tables T;
+  unsigned char* KVs = Qs + TILE;  // [2 buffers][K | V]
   const int p = blockIdx.y, h = blockIdx.z, qb = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   Tables t;
-  build_tables<WINDOW>(t, Vs + 64 * PITCH, P, p, h, nq_pad, nk_pad);
+  build_tables<WINDOW>(t, KVs + 4 * TILE, P, p, h, nq_pad, nk_pad);
   __syncthreads();
   const int col0 = h * HD;
-  load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
+  load_tile_async<HD>(Qs, P.Q, P.ldq, col0, t.qrow_s, qb * BQ);
+  load_tile_async<HD>(KVs, P.K, P.ldk, col0, t.krow_s, 0);
+  load_tile_async<HD>(KVs + TILE, P.V, P.ldv, col0, t.krow_s, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   uint32_t qf[HD / 16][4];
   {
@@ -173,12 +231,21 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
   const int i0 = qb * BQ + warp * 16 + g;  // rows i0 and i0+8
   const float sc2 = P.scale * LOG2E;
+  const uint32_t qinf[2] = {t.qinfo[i0], t.qinfo[i0 + 8]};
   const int nkb = (t.nk + BKEY - 1) / BKEY;
   for (int kb = 0; kb < nkb; ++kb) {
-    __syncthreads();
-    load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
-    load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
-    __syncthreads();
+    unsigned char* Ks = KVs + (kb & 1) * 2 * TILE;
+    unsigned char* Vs = Ks + TILE;
+    if (kb > 0) {  // block kb was prefetched during block kb-1
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    if (kb + 1 < nkb) {  // prefetch the next K/V block into the other buffer (its readers finished at the barrier above)
+      unsigned char* Kn = KVs + ((kb + 1) & 1) * 2 * TILE;
+      load_tile_async<HD>(Kn, P.K, P.ldk, col0, t.krow_s, (kb + 1) * BKEY);
+      load_tile_async<HD>(Kn + TILE, P.V, P.ldv, col0, t.krow_s, (kb + 1) * BKEY);
+      cp_async_commit();
+    }
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -196,16 +263,20 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
     }
     // scale + bias/mask (log2 domain), running max
     float mnew[2] = {mrow[0], mrow[1]};
+    const bool ragged = (kb + 1) * BKEY > t.nk;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 8; ++nt) {
+      const int jb = kb * BKEY + nt * 8 + t4 * 2;
+      const uint2 kj = lds_v2u32(t.kinfo_s + 4u * (uint32_t)jb);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int i = i0 + (e >> 1) * 8, j = kb * BKEY + nt * 8 + t4 * 2 + (e & 1);
-        float v = -INFINITY;
-        if (j < t.nk && i < t.nq) v = s[nt][e] * sc2 + add_term<WINDOW>(t, i, j) * LOG2E;
+        const uint32_t kw = (e & 1) ? kj.y : kj.x;
+        float v = score2<WINDOW>(t, s[nt][e], sc2, qinf[e >> 1], kw, i0 + (e >> 1) * 8, jb + (e & 1));
+        if (ragged && (kw >> 31)) v = -INFINITY;
         s[nt][e] = v;
         mnew[e >> 1] = fmaxf(mnew[e >> 1], v);
       }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
@@ -226,7 +297,7 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f(s[nt][e] - msafe[e >> 1]);
+        const float pv = fast_exp2(s[nt][e] - msafe[e >> 1]);
         s[nt][e] = pv;
         lrow[e >> 1] += pv;
       }
@@ -275,35 +346,41 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
 //               of the MMA already in A-operand layout: dV += P^T.dO, dK += dS^T.Q
 // ==========================================================================================
 template <int HD, bool WINDOW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int nk_pad) {
-  constexpr int PITCH = HD * 2 + 16;
+  constexpr int PITCH = HD * 2 + 16, TILE = 64 * PITCH;
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* Qs = smem;
-  unsigned char* dOs = Qs + 64 * PITCH;
-  unsigned char* Ks = dOs + 64 * PITCH;
-  unsigned char* Vs = Ks + 64 * PITCH;
-  float* lse_s = (float*)(Vs + 64 * PITCH);  // [64]
+  unsigned char* dOs = Qs + TILE;
+  unsigned char* KVs = dOs + TILE;             // [2 buffers][K | V]
+  float* lse_s = (float*)(KVs + 4 * TILE);     // [64]
   float* del_s = lse_s + 64;                 // [64]
-  float* dtab_s = del_s + 64;                // window: [n_rel]
+  // window: bias-table gradient in shared memory.  fp32 (and 64-bit) shared atomics compile to a
+  // compare-and-swap spin loop, so the key order is chosen (build_tables) to make the 32 lanes of a fragment
+  // hit distinct slots: the loop then succeeds on its first trip.
+  float* dtab_s = del_s + 64;  // [n_rel]
   const int p = blockIdx.y, h = blockIdx.z, qb = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   int n_rel = 0;
   if (WINDOW) n_rel = (2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
   Tables t;
-  build_tables<WINDOW>(t, (unsigned char*)(dtab_s + n_rel), P, p, h, nq_pad, nk_pad);
+  build_tables<WINDOW>(t, (unsigned char*)(((uintptr_t)(dtab_s + n_rel) + 15) & ~(uintptr_t)15), P, p, h, nq_pad, nk_pad);
   for (int i = threadIdx.x; i < n_rel; i += blockDim.x) dtab_s[i] = 0.f;
   __syncthreads();
   const int col0 = h * HD;
-  load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
-  load_tile<HD>(dOs, P.dO, P.ldo, col0, t.qrow, qb * BQ);
-  load_tile<HD>(Ks, P.O, P.ldo, col0, t.qrow, qb * BQ);  // O tile, only for delta
+  load_tile_async<HD>(Qs, P.Q, P.ldq, col0, t.qrow_s, qb * BQ);
+  load_tile_async<HD>(dOs, P.dO, P.ldo, col0, t.qrow_s, qb * BQ);
+  load_tile_async<HD>(KVs + 2 * TILE, P.O, P.ldo, col0, t.qrow_s, qb * BQ);  // O tile (buffer 1), only for delta
+  load_tile_async<HD>(KVs, P.K, P.ldk, col0, t.krow_s, 0);                   // first K/V block (buffer 0)
+  load_tile_async<HD>(KVs + TILE, P.V, P.ldv, col0, t.krow_s, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   {  // delta_i = sum_d dO[i,d] * O[i,d] : two threads per row
     const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
     float d = 0.f;
     const __nv_bfloat162* a = (const __nv_bfloat162*)(dOs + r * PITCH + hf * HD);
-    const __nv_bfloat162* b = (const __nv_bfloat162*)(Ks + r * PITCH + hf * HD);
+    const __nv_bfloat162* b = (const __nv_bfloat162*)(KVs + 2 * TILE + r * PITCH + hf * HD);
 #pragma unroll
     for (int c = 0; c < HD / 4; ++c) {
       const float2 fa = __bfloat1622float2(a[c]), fb = __bfloat1622float2(b[c]);
@@ -327,15 +404,28 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   float dq[HD / 8][4];
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-  const float sc = P.scale;
+  const float sc = P.scale, sc2 = P.scale * LOG2E;
   const int il = warp * 16 + g;
   const int i0 = qb * BQ + il;
   const int nkb = (t.nk + BKEY - 1) / BKEY;
+  __syncthreads();  // lse_s / del_s visible
+  // padding query rows (i >= nq) get lse = +inf -> p = 0 -> no gradient, no bias-table contribution
+  const uint32_t qinf[2] = {t.qinfo[i0], t.qinfo[i0 + 8]};
+  const float lse2[2] = {i0 < t.nq ? lse_s[il] * LOG2E : INFINITY, i0 + 8 < t.nq ? lse_s[il + 8] * LOG2E : INFINITY};
+  const float del[2] = {del_s[il], del_s[il + 8]};
   for (int kb = 0; kb < nkb; ++kb) {
-    __syncthreads();
-    load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
-    load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
-    __syncthreads();
+    unsigned char* Ks = KVs + (kb & 1) * 2 * TILE;
+    unsigned char* Vs = Ks + TILE;
+    if (kb > 0) {
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    if (kb + 1 < nkb) {  // (the barrier before this loop / above guarantees the other buffer is no longer read)
+      unsigned char* Kn = KVs + ((kb + 1) & 1) * 2 * TILE;
+      load_tile_async<HD>(Kn, P.K, P.ldk, col0, t.krow_s, (kb + 1) * BKEY);
+      load_tile_async<HD>(Kn + TILE, P.V, P.ldv, col0, t.krow_s, (kb + 1) * BKEY);
+      cp_async_commit();
+    }
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -354,20 +444,21 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
         mma16816(dp[nt + 1], dof[ks], b + 2);
       }
     uint32_t dsf[4][4];
+    const bool ragged = (kb + 1) * BKEY > t.nk;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      const int jb = kb * BKEY + nt * 8 + t4 * 2;
+      const uint2 kj = lds_v2u32(t.kinfo_s + 4u * (uint32_t)jb);
       float ds[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int rr = (e >> 1) * 8;
-        const int i = i0 + rr, j = kb * BKEY + nt * 8 + t4 * 2 + (e & 1);
-        float d = 0.f;
-        if (i < t.nq && j < t.nk) {
-          const float sv = s[nt][e] * sc + add_term<WINDOW>(t, i, j);
-          const float pr = __expf(sv - lse_s[il + rr]);
-          d = pr * (dp[nt][e] - del_s[il + rr]);
-          if (WINDOW) atomicAdd(&dtab_s[t.code[i] - t.code[j] + t.center], d);
-        }
+        const int r = e >> 1;
+        const uint32_t kw = (e & 1) ? kj.y : kj.x;
+        const float v = score2<WINDOW>(t, s[nt][e], sc2, qinf[r], kw, i0 + r * 8, jb + (e & 1));
+        float pr = fast_exp2(v - lse2[r]);
+        if (ragged && (kw >> 31)) pr = 0.f;
+        const float d = pr * (dp[nt][e] - del[r]);
+        if (WINDOW) atomicAdd(&dtab_s[(int)(qinf[r] & 0xffffu) - (int)(kw & 0xffffu)], d);
         ds[e] = d * sc;
       }
       dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
@@ -403,15 +494,14 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
 }
 
 template <int HD, bool WINDOW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pad, int nk_pad) {
-  constexpr int PITCH = HD * 2 + 16;
+  constexpr int PITCH = HD * 2 + 16, TILE = 64 * PITCH;
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* Ks = smem;
-  unsigned char* Vs = Ks + 64 * PITCH;
-  unsigned char* Qs = Vs + 64 * PITCH;
-  unsigned char* dOs = Qs + 64 * PITCH;
-  float* lse_s = (float*)(dOs + 64 * PITCH);  // [nq_pad]
+  unsigned char* Vs = Ks + TILE;
+  unsigned char* QDs = Vs + TILE;               // [2 buffers][Q | dO]
+  float* lse_s = (float*)(QDs + 4 * TILE);      // [nq_pad]
   float* del_s = lse_s + nq_pad;              // [nq_pad]
   const int p = blockIdx.y, h = blockIdx.z, kb = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
@@ -422,11 +512,15 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
   const int col0 = h * HD;
   for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {
     const bool ok = i < t.nq;
-    lse_s[i] = ok ? P.lse[((size_t)p * P.H + h) * P.Nq + i] : 0.f;
+    lse_s[i] = ok ? P.lse[((size_t)p * P.H + h) * P.Nq + i] * LOG2E : INFINITY;  // log2 domain; +inf kills padding
     del_s[i] = ok ? delta[((size_t)p * P.H + h) * P.Nq + i] : 0.f;
   }
-  load_tile<HD>(Ks, P.K, P.ldk, col0, t.krow, kb * BKEY);
-  load_tile<HD>(Vs, P.V, P.ldv, col0, t.krow, kb * BKEY);
+  load_tile_async<HD>(Ks, P.K, P.ldk, col0, t.krow_s, kb * BKEY);
+  load_tile_async<HD>(Vs, P.V, P.ldv, col0, t.krow_s, kb * BKEY);
+  load_tile_async<HD>(QDs, P.Q, P.ldq, col0, t.qrow_s, 0);
+  load_tile_async<HD>(QDs + TILE, P.dO, P.ldo, col0, t.qrow_s, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   const int m8 = lane >> 3, r8 = lane & 7;
   uint32_t kf[HD / 16][4], vf[HD / 16][4];
@@ -440,14 +534,23 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
   for (int i = 0; i < HD / 8; ++i)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
-  const float sc = P.scale;
-  const int j0 = kb * BKEY + warp * 16 + g;  // keys j0 and j0+8
+  const float sc = P.scale, sc2 = P.scale * LOG2E;
+  const int j0 = kb * BKEY + warp * 16 + g;  // keys j0 and j0+8 (padding keys: K/V rows are zero, results dropped)
+  const uint32_t kinf[2] = {t.kinfo[j0], t.kinfo[j0 + 8]};
   const int nqb = (t.nq + BQ - 1) / BQ;
   for (int qb = 0; qb < nqb; ++qb) {
-    __syncthreads();
-    load_tile<HD>(Qs, P.Q, P.ldq, col0, t.qrow, qb * BQ);
-    load_tile<HD>(dOs, P.dO, P.ldo, col0, t.qrow, qb * BQ);
-    __syncthreads();
+    unsigned char* Qs = QDs + (qb & 1) * 2 * TILE;
+    unsigned char* dOs = Qs + TILE;
+    if (qb > 0) {
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    if (qb + 1 < nqb) {
+      unsigned char* Qn = QDs + ((qb + 1) & 1) * 2 * TILE;
+      load_tile_async<HD>(Qn, P.Q, P.ldq, col0, t.qrow_s, (qb + 1) * BQ);
+      load_tile_async<HD>(Qn + TILE, P.dO, P.ldo, col0, t.qrow_s, (qb + 1) * BQ);
+      cp_async_commit();
+    }
     float s[8][4], dp[8][4];  // rows = keys (g, g+8), cols = queries of this block
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -468,19 +571,19 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
     uint32_t pf[4][4], dsf[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      const int ib = qb * BQ + nt * 8 + t4 * 2;   // two consecutive queries (columns of S^T)
+      const uint2 qi2 = lds_v2u32(t.qinfo_s + 4u * (uint32_t)ib);
+      const float2 l2 = *(const float2*)(lse_s + ib);
+      const float2 d2 = *(const float2*)(del_s + ib);
       float pv[4], ds[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int j = j0 + (e >> 1) * 8;
-        const int i = qb * BQ + nt * 8 + t4 * 2 + (e & 1);
-        float pr = 0.f, d = 0.f;
-        if (i < t.nq && j < t.nk) {
-          const float sv = s[nt][e] * sc + add_term<WINDOW>(t, i, j);
-          pr = __expf(sv - lse_s[i]);
-          d = pr * (dp[nt][e] - del_s[i]);
-        }
+        const int r = e >> 1;
+        const uint32_t qw = (e & 1) ? qi2.y : qi2.x;
+        const float v = score2<WINDOW>(t, s[nt][e], sc2, qw, kinf[r], ib + (e & 1), j0 + r * 8);
+        const float pr = fast_exp2(v - ((e & 1) ? l2.y : l2.x));   // padding queries carry lse = +inf -> 0
         pv[e] = pr;
-        ds[e] = d * sc;
+        ds[e] = pr * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * sc;
       }
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
       pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
@@ -533,16 +636,16 @@ template <int HD, bool WINDOW>
 static size_t table_bytes(const AttnParams& P, int nq_pad, int nk_pad) {
   if (WINDOW) {
     const int n_rel = (2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
-    return sizeof(int) * nq_pad + sizeof(short) * nq_pad + (nq_pad + 15) / 16 * 16 + sizeof(float) * n_rel;
+    return sizeof(int) * 4 * nq_pad + sizeof(float) * n_rel;
   }
-  return sizeof(int) * (nq_pad + nk_pad) + nk_pad;
+  return sizeof(int) * 2 * (nq_pad + nk_pad);
 }
 
 template <int HD, bool WINDOW>
 static int launch_fwd(const AttnParams& P, int Pn, int nq, int max_nk, cudaStream_t st) {
   constexpr int PITCH = HD * 2 + 16;
   const int nq_pad = pad64(nq), nk_pad = pad64(max_nk);
-  const size_t smem = 3 * 64 * PITCH + table_bytes<HD, WINDOW>(P, nq_pad, nk_pad) + 16;
+  const size_t smem = 5 * 64 * PITCH + table_bytes<HD, WINDOW>(P, nq_pad, nk_pad) + 16;
   auto kern = attn_mma_fwd_kernel<HD, WINDOW>;
   if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nq_pad / 64, Pn, P.H);
@@ -558,7 +661,7 @@ static int launch_bwd(const AttnParams& P, float* delta, int Pn, int nq, int max
   if (WINDOW) n_rel = (size_t)(2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
   const size_t tb = table_bytes<HD, WINDOW>(P, nq_pad, nk_pad);
   {
-    const size_t smem = 4 * 64 * PITCH + sizeof(float) * (128 + n_rel) + tb + 16;
+    const size_t smem = 6 * 64 * PITCH + sizeof(float) * (128 + n_rel) + tb + 32;
     auto kern = attn_mma_bwd_dq_kernel<HD, WINDOW>;
     if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nq_pad / 64, Pn, P.H);
@@ -566,7 +669,7 @@ static int launch_bwd(const AttnParams& P, float* delta, int Pn, int nq, int max
     if (check_launch("attn_mma_bwd_dq_kernel")) return 1;
   }
   {
-    const size_t smem = 4 * 64 * PITCH + sizeof(float) * 2 * nq_pad + tb + 16;
+    const size_t smem = 6 * 64 * PITCH + sizeof(float) * 2 * nq_pad + tb + 16;
     auto kern = attn_mma_bwd_dkv_kernel<HD, WINDOW>;
     if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nk_pad / 64, Pn, P.H);

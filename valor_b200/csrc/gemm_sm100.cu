@@ -15,6 +15,7 @@
 // or red.global.add.v4.f32 for split-K weight-gradient accumulation).
 #include "common.cuh"
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace valor {
 
@@ -91,24 +92,103 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Epilogue specialisations of the TMA-store path (compile-time: no per-element branching).
+//   PLAIN    : bias
+//   RES      : bias + residual
+//   GELU_PRE : bias, pre-activation side output, erf-GELU
+//   GELU_AUX : * GELU'(aux)   (dgrad through the activation)
+//   GENERIC  : everything decided at run time (other activations, odd combinations)
+enum EpiMode { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES = 2, EPI_GELU_PRE = 3, EPI_GELU_AUX = 4 };
+
+// One 32-column slab of one accumulator row: v (raw TMEM words) -> staging row(s) in shared memory.
+template <int MODE>
+__device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, const GemmEpilogue& ep, int row, int col0, int M,
+                                         int N, int lane, int sub, uint8_t* st_out, uint8_t* st_pre) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float xg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xg[j] = fmaf(__uint_as_float(v[g * 8 + j]), ep.alpha, wb[g * 8 + j]);
+    const int col = col0 + g * 8;
+    const int chunk = sub * 4 + g;  // 16-byte chunk inside the 128-byte staging row
+    const uint32_t soff = (uint32_t)lane * 128u + (uint32_t)((chunk ^ (lane & 7)) << 4);
+    const bool inb = row < M && col + 8 <= N;
+    const bool want_pre = (MODE == EPI_GELU_PRE) || (MODE == EPI_GENERIC && ep.preact_out != nullptr);
+    if (want_pre) {
+      uint4 pk;
+      __nv_bfloat162* h = (__nv_bfloat162*)&pk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
+      *(uint4*)(st_pre + soff) = pk;
+    }
+    const bool use_aux = (MODE == EPI_GELU_AUX) || (MODE == EPI_GENERIC && ep.act_aux != nullptr);
+    if (use_aux) {
+      const int act = (MODE == EPI_GELU_AUX) ? VALOR_ACT_GELU : ep.act;
+      if (inb) {
+        uint4 a = *(const uint4*)((const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col);
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(h[j]);
+          xg[2 * j] *= act_grad(f.x, act);
+          xg[2 * j + 1] *= act_grad(f.y, act);
+        }
+      } else if (row < M) {
+        for (int j = 0; j < 8 && col + j < N; ++j)
+          xg[j] *= act_grad(__bfloat162float(((const bf16*)ep.act_aux)[(size_t)row * ep.ld_aux + col + j]), act);
+      }
+    } else if (MODE == EPI_GELU_PRE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], VALOR_ACT_GELU);
+    } else if (MODE == EPI_GENERIC) {
+      if (ep.act != VALOR_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
+      }
+    }
+    const bool use_res = (MODE == EPI_RES) || (MODE == EPI_GENERIC && ep.residual != nullptr);
+    if (use_res) {
+      if (inb) {
+        uint4 r = *(const uint4*)((const bf16*)ep.residual + (size_t)row * ep.ldr + col);
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(h[j]);
+          xg[2 * j] += f.x;
+          xg[2 * j + 1] += f.y;
+        }
+      } else if (row < M) {
+        for (int j = 0; j < 8 && col + j < N; ++j)
+          xg[j] += __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col + j]);
+      }
+    }
+    uint4 pk;
+    __nv_bfloat162* h = (__nv_bfloat162*)&pk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
+    *(uint4*)(st_out + soff) = pk;
+  }
+}
+
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 4 * 16384;  // per epilogue half: 128x64 bf16 out tile + pre-activation tile
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - BLOCK_N * 4 /*bias*/ - STAGING_BYTES;
+  static constexpr int BIAS_BYTES = 4096;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - BIAS_BYTES - STAGING_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BLOCK_N * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES;
 };
 
-template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR>
+template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __launch_bounds__(384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                   void* __restrict__ Cptr, long long ldc, int M, int N, int K, int k_splits, int vec_ok,
-                  int tma_store, GemmEpilogue ep) {
+                  int tma_store, int dbg, GemmEpilogue ep) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -242,9 +322,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = e >> 2;
     const int et = threadIdx.x - 128;           // 0..255
     const int r_tile = q * 32 + lane;           // row inside the 128-row tile
-    const bool issuer = (q == 0 && lane == 0);  // one thread per half drives the TMA stores
-    uint8_t* st_out = staging + half * 32768;
-    uint8_t* st_pre = st_out + 16384;
+    // TMA-store path: every warp owns a private 2 x 4 KB staging slab (its 32 rows x 64 columns), a private
+    // bias slice and issues its own bulk stores: no CTA-level barrier anywhere in the epilogue.
+    uint8_t* wst = staging + e * 8192;
+    float* wbias = bias_s + e * 128;
+    const bool has_pre = ep.preact_out != nullptr;
+    uint32_t chunk_ctr = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -254,99 +337,71 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ks = rest % k_splits;
       const int n0 = n_blk * BLOCK_N;
       const int row = m_blk * BLOCK_M + r_tile;
-      // stage the bias slice (only split 0 adds bias when split-K accumulates)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = et; i < BLOCK_N; i += 256) {
-        float b = 0.f;
-        if (ep.bias != nullptr && ks == 0 && n0 + i < N) b = ep.bias[n0 + i];
-        bias_s[i] = b;
+      if (!tma_store) {
+        // stage the bias slice (only split 0 adds bias when split-K accumulates)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < BLOCK_N; i += 256) {
+          float b = 0.f;
+          if (ep.bias != nullptr && ks == 0 && n0 + i < N) b = ep.bias[n0 + i];
+          bias_s[i] = b;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      if (tma_store) {
+      if (!tma_store || (dbg & 1)) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+      }
+      if (dbg & 1) {
+        // (diagnostic) mainloop only: release the accumulator without reading it
+      } else if (tma_store) {
         // ---------- bf16 output through swizzled smem staging + TMA store (coalesced, OOB-clipped) ----------
+        // bias for all of this warp's chunks of the tile, fetched before the accumulator is ready
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < (BLOCK_N / 64 + 1) / 2; ++cc) {
+          const int cb = n0 + (half + 2 * cc) * 64 + lane;
+          wbias[cc * 64 + lane] = (ep.bias != nullptr && cb < N) ? ep.bias[cb] : 0.f;
+          wbias[cc * 64 + 32 + lane] = (ep.bias != nullptr && cb + 32 < N) ? ep.bias[cb + 32] : 0.f;
+        }
+        __syncwarp();
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+        uint32_t va[32], vb[32];
+        if (n0 + half * 64 < N) {  // first chunk's accumulator slabs in flight
+          tmem_ld_32x32(trow + half * 64, va);
+          tmem_ld_32x32(trow + half * 64 + 32, vb);
+        }
 #pragma unroll 1
-        for (int c = half; c < BLOCK_N / 64; c += 2) {
+        for (int c = half, cc = 0; c < BLOCK_N / 64; c += 2, ++cc) {
           if (n0 + c * 64 >= N) break;
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-          else asm volatile("bar.sync 3, 128;" ::: "memory");
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 64 + sub * 32, v);
-            tmem_ld_wait();
-            const int col0 = n0 + c * 64 + sub * 32;
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 64 + sub * 32 + j];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              float* xg = x + g * 8;
-              const int chunk = sub * 4 + g;  // 16-byte chunk inside the 128-byte staging row
-              const uint32_t soff = (uint32_t)r_tile * 128u + (uint32_t)((chunk ^ (r_tile & 7)) << 4);
-              if (ep.preact_out != nullptr) {
-                uint4 pk;
-                __nv_bfloat162* h = (__nv_bfloat162*)&pk;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
-                *(uint4*)(st_pre + soff) = pk;
-              }
-              const bool inb = row < M && col + 8 <= N;
-              if (ep.act_aux != nullptr) {
-                if (inb) {
-                  uint4 a = *(const uint4*)((const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col);
-                  const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float2 f = __bfloat1622float2(h[j]);
-                    xg[2 * j] *= act_grad(f.x, ep.act);
-                    xg[2 * j + 1] *= act_grad(f.y, ep.act);
-                  }
-                } else if (row < M) {
-                  for (int j = 0; j < 8 && col + j < N; ++j)
-                    xg[j] *= act_grad(__bfloat162float(((const bf16*)ep.act_aux)[(size_t)row * ep.ld_aux + col + j]), ep.act);
-                }
-              } else if (ep.act != VALOR_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
-              }
-              if (ep.residual != nullptr) {
-                if (inb) {
-                  uint4 r = *(const uint4*)((const bf16*)ep.residual + (size_t)row * ep.ldr + col);
-                  const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float2 f = __bfloat1622float2(h[j]);
-                    xg[2 * j] += f.x;
-                    xg[2 * j + 1] += f.y;
-                  }
-                } else if (row < M) {
-                  for (int j = 0; j < 8 && col + j < N; ++j)
-                    xg[j] += __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col + j]);
-                }
-              }
-              uint4 pk;
-              __nv_bfloat162* h = (__nv_bfloat162*)&pk;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(xg[2 * j], xg[2 * j + 1]);
-              *(uint4*)(st_out + soff) = pk;
-            }
+          // staging: [out | pre] when the pre-activation side output exists (single-buffered), otherwise the
+          // two buffers alternate so the TMA store of chunk i overlaps the TMEM reads / math of chunk i+1
+          uint8_t* st_out = wst + ((!has_pre && (chunk_ctr & 1)) ? 4096 : 0);
+          uint8_t* st_pre = wst + 4096;
+          ++chunk_ctr;
+          if (lane == 0) {
+            if (has_pre) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
+          tmem_ld_wait();
+          __syncwarp();
+          const bool more = (c + 2 < BLOCK_N / 64) && (n0 + (c + 2) * 64 < N);
+          epi_slab<MODE>(va, wbias + cc * 64, ep, row, n0 + c * 64, M, N, lane, 0, st_out, st_pre);
+          if (more) tmem_ld_32x32(trow + (c + 2) * 64, va);       // next chunk's slabs stream in while this one
+          epi_slab<MODE>(vb, wbias + cc * 64 + 32, ep, row, n0 + c * 64 + 32, M, N, lane, 1, st_out, st_pre);
+          if (more) tmem_ld_32x32(trow + (c + 2) * 64 + 32, vb);  // is converted, staged and stored
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-          else asm volatile("bar.sync 3, 128;" ::: "memory");
-          if (issuer) {
+          __syncwarp();
+          if (lane == 0 && !(dbg & 2)) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              (uint64_t)&tmC),
-                         "r"(smem_u32(st_out)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M)
+                         "r"(smem_u32(st_out)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M + q * 32)
                          : "memory");
-            if (ep.preact_out != nullptr)
+            if (has_pre)
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                (uint64_t)&tmP),
-                           "r"(smem_u32(st_pre)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M)
+                           "r"(smem_u32(st_pre)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M + q * 32)
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -426,7 +481,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (tma_store && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -469,30 +524,32 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
-template <int BN, bool AK, bool BK>
+template <int BN, bool AK, bool BK, int MODE>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, void* C,
                       long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
                       const GemmEpilogue& ep, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_sm100_kernel<BN, AK, BK>;
+  auto kern = gemm_sm100_kernel<BN, AK, BK, MODE>;
   static bool attr_done = false;
   if (!attr_done) {
     VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("VALOR_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, dbg, ep);
   return check_launch("gemm_sm100_kernel");
 }
 
-template <bool AK, bool BK>
+template <bool AK, bool BK, int MODE>
 static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      void* C, long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
                      const GemmEpilogue& ep, int grid, cudaStream_t st) {
   switch (bn) {
-    case 64: return launch_cfg<64, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-    case 128: return launch_cfg<128, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-    case 192: return launch_cfg<192, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-    default: return launch_cfg<256, AK, BK>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    case 64: return launch_cfg<64, AK, BK, MODE>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    case 128: return launch_cfg<128, AK, BK, MODE>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    case 192: return launch_cfg<192, AK, BK, MODE>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    default: return launch_cfg<256, AK, BK, MODE>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
   }
 }
 
@@ -568,15 +625,40 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   memset(&tc, 0, sizeof(tc));
   memset(&tp, 0, sizeof(tp));
   if (tma_store) {
-    if (make_tmap(&tc, C, N, M, ldc, BLOCK_M)) return 1;
-    if (ep.preact_out && make_tmap(&tp, ep.preact_out, N, M, ep.ld_pre, BLOCK_M)) return 1;
+    if (make_tmap(&tc, C, N, M, ldc, 32)) return 1;
+    if (ep.preact_out && make_tmap(&tp, ep.preact_out, N, M, ep.ld_pre, 32)) return 1;
   }
   const long total = (long)m_blocks * n_blocks * k_splits;
   const int grid = (int)(total < sms ? total : sms);
-  if (a_kmajor && b_kmajor) return launch_bn<true, true>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-  if (a_kmajor && !b_kmajor) return launch_bn<true, false>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-  if (!a_kmajor && b_kmajor) return launch_bn<false, true>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-  return launch_bn<false, false>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+  // epilogue specialisation (TMA-store path only; everything else runs the generic code)
+  int mode = EPI_GENERIC;
+  if (tma_store) {
+    const bool res = ep.residual != nullptr, aux = ep.act_aux != nullptr, pre = ep.preact_out != nullptr;
+    if (!res && !aux && !pre && ep.act == VALOR_ACT_NONE) mode = EPI_PLAIN;
+    else if (res && !aux && !pre && ep.act == VALOR_ACT_NONE) mode = EPI_RES;
+    else if (!res && !aux && pre && ep.act == VALOR_ACT_GELU) mode = EPI_GELU_PRE;
+    else if (!res && aux && !pre && ep.act == VALOR_ACT_GELU && ep.bias == nullptr) mode = EPI_GELU_AUX;
+  }
+#define VALOR_LAUNCH(AK, BK, MODE) \
+  return launch_bn<AK, BK, MODE>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st)
+  if (a_kmajor && b_kmajor) {
+    switch (mode) {
+      case EPI_PLAIN: VALOR_LAUNCH(true, true, EPI_PLAIN);
+      case EPI_RES: VALOR_LAUNCH(true, true, EPI_RES);
+      case EPI_GELU_PRE: VALOR_LAUNCH(true, true, EPI_GELU_PRE);
+      default: VALOR_LAUNCH(true, true, EPI_GENERIC);
+    }
+  }
+  if (a_kmajor && !b_kmajor) {
+    switch (mode) {
+      case EPI_PLAIN: VALOR_LAUNCH(true, false, EPI_PLAIN);
+      case EPI_GELU_AUX: VALOR_LAUNCH(true, false, EPI_GELU_AUX);
+      default: VALOR_LAUNCH(true, false, EPI_GENERIC);
+    }
+  }
+  if (!a_kmajor && b_kmajor) VALOR_LAUNCH(false, true, EPI_GENERIC);
+  VALOR_LAUNCH(false, false, EPI_GENERIC);
+#undef VALOR_LAUNCH
 }
 
 }  // namespace valor
