@@ -168,9 +168,12 @@ def main_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"VALOR-base pretrain step (Swin-B+AST+BERT), oracle port of the reference on host "
-                                   f"CPU, B=2 F={args.frames} A={args.clips} T={args.tokens}", "task": TASK,
-                       "dropout": "off"},
+            "config": {"workload": f"VALOR-base (VideoSwin-B + AST + BERT-base fusion) pretrain step, per-GPU batch "
+                                   f"{args.batch}, {args.frames} frames 224^2, {args.clips} audio clips, {args.tokens} "
+                                   f"tokens (BASELINE configs[1])", "task": TASK, "global_batch": args.batch,
+                       "parallelism": "cpu", "dropout": "off (parity mode)", "geom": args.geom,
+                       "sample": f"each step = one full training step of the same per-sample workload at B=2 "
+                                 f"(samples/s is per-sample throughput; B={args.batch} would take minutes per step on CPU)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -20,15 +20,17 @@ def main(path, skip=0, top=40):
         us = v / 1000.0 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1000.0 if u in ("ms", "msecond") else v)
         rows.append((r[ki], us))
     rows = rows[skip:]
-    agg = defaultdict(lambda: [0, 0.0])
+    agg = defaultdict(lambda: [0, 0.0, 0.0, 1e30])
     for k, us in rows:
         name = re.sub(r"\(.*", "", k).replace("void ", "").replace("valor::", "")
         agg[name][0] += 1
         agg[name][1] += us
+        agg[name][2] = max(agg[name][2], us)
+        agg[name][3] = min(agg[name][3], us)
     total = sum(v[1] for v in agg.values())
     print(f"launches {len(rows)}  total {total/1000:.2f} ms")
-    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-        print(f"{us/1000:9.3f} ms {100*us/total:5.1f}%  n={n:5d}  avg {us/n:9.1f} us  {name[:110]}")
+    for name, (n, us, mx, mn) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"{us/1000:9.3f} ms {100*us/total:5.1f}%  n={n:5d}  avg {us/n:9.1f} us  min {mn:8.1f} max {mx:9.1f}  {name[:100]}")
 
 
 if __name__ == "__main__":

@@ -346,7 +346,7 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
 //               of the MMA already in A-operand layout: dV += P^T.dO, dK += dS^T.Q
 // ==========================================================================================
 template <int HD, bool WINDOW>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int nk_pad) {
   constexpr int PITCH = HD * 2 + 16, TILE = 64 * PITCH;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -355,17 +355,19 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   unsigned char* KVs = dOs + TILE;             // [2 buffers][K | V]
   float* lse_s = (float*)(KVs + 4 * TILE);     // [64]
   float* del_s = lse_s + 64;                 // [64]
-  // window: bias-table gradient in shared memory.  fp32 (and 64-bit) shared atomics compile to a
-  // compare-and-swap spin loop, so the key order is chosen (build_tables) to make the 32 lanes of a fragment
-  // hit distinct slots: the loop then succeeds on its first trip.
-  float* dtab_s = del_s + 64;  // [n_rel]
+  // window: bias-table gradient in shared memory.  Only 32-bit INTEGER shared atomics are native (fp32 and
+  // 64-bit ones compile to compare-and-swap spin loops, which dominated this kernel), so each slot is a
+  // 64-bit two's-complement fixed-point sum (scale 2^40) kept as two words: ATOMS.ADD on the low word returns
+  // the old value, the carry is folded into the ATOMS.ADD on the high word.  Integer adds commute: the result
+  // is exact and order-independent.
+  uint32_t* dtab_s = (uint32_t*)(del_s + 64);  // [n_rel][2] : lo, hi words of a 64-bit fixed-point sum
   const int p = blockIdx.y, h = blockIdx.z, qb = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   int n_rel = 0;
   if (WINDOW) n_rel = (2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
   Tables t;
-  build_tables<WINDOW>(t, (unsigned char*)(((uintptr_t)(dtab_s + n_rel) + 15) & ~(uintptr_t)15), P, p, h, nq_pad, nk_pad);
-  for (int i = threadIdx.x; i < n_rel; i += blockDim.x) dtab_s[i] = 0.f;
+  build_tables<WINDOW>(t, (unsigned char*)(((uintptr_t)(dtab_s + 2 * n_rel) + 15) & ~(uintptr_t)15), P, p, h, nq_pad, nk_pad);
+  for (int i = threadIdx.x; i < 2 * n_rel; i += blockDim.x) dtab_s[i] = 0u;
   __syncthreads();
   const int col0 = h * HD;
   load_tile_async<HD>(Qs, P.Q, P.ldq, col0, t.qrow_s, qb * BQ);
@@ -426,53 +428,62 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
       load_tile_async<HD>(Kn + TILE, P.V, P.ldv, col0, t.krow_s, (kb + 1) * BKEY);
       cp_async_commit();
     }
-    float s[8][4], dp[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks)
-#pragma unroll
-      for (int nt = 0; nt < 8; nt += 2) {
-        uint32_t b[4];
-        ldsm_x4(b, s_u32(Ks + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-        mma16816(s[nt], qf[ks], b);
-        mma16816(s[nt + 1], qf[ks], b + 2);
-        ldsm_x4(b, s_u32(Vs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-        mma16816(dp[nt], dof[ks], b);
-        mma16816(dp[nt + 1], dof[ks], b + 2);
-      }
-    uint32_t dsf[4][4];
     const bool ragged = (kb + 1) * BKEY > t.nk;
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {  // two 32-key halves: halves the live accumulator registers
+      float s[4][4], dp[4][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int jb = kb * BKEY + nt * 8 + t4 * 2;
-      const uint2 kj = lds_v2u32(t.kinfo_s + 4u * (uint32_t)jb);
-      float ds[4];
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = e >> 1;
-        const uint32_t kw = (e & 1) ? kj.y : kj.x;
-        const float v = score2<WINDOW>(t, s[nt][e], sc2, qinf[r], kw, i0 + r * 8, jb + (e & 1));
-        float pr = fast_exp2(v - lse2[r]);
-        if (ragged && (kw >> 31)) pr = 0.f;
-        const float d = pr * (dp[nt][e] - del[r]);
-        if (WINDOW) atomicAdd(&dtab_s[(int)(qinf[r] & 0xffffu) - (int)(kw & 0xffffu)], d);
-        ds[e] = d * sc;
+        for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt += 2) {
+          uint32_t b[4];
+          ldsm_x4(b, s_u32(Ks + ((hh * 4 + nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+          mma16816(s[nt], qf[ks], b);
+          mma16816(s[nt + 1], qf[ks], b + 2);
+          ldsm_x4(b, s_u32(Vs + ((hh * 4 + nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+          mma16816(dp[nt], dof[ks], b);
+          mma16816(dp[nt + 1], dof[ks], b + 2);
+        }
+      uint32_t dsf[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int jb = kb * BKEY + (hh * 4 + nt) * 8 + t4 * 2;
+        const uint2 kj = lds_v2u32(t.kinfo_s + 4u * (uint32_t)jb);
+        float ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const uint32_t kw = (e & 1) ? kj.y : kj.x;
+          const float v = score2<WINDOW>(t, s[nt][e], sc2, qinf[r], kw, i0 + r * 8, jb + (e & 1));
+          float pr = fast_exp2(v - lse2[r]);
+          if (ragged && (kw >> 31)) pr = 0.f;
+          const float d = pr * (dp[nt][e] - del[r]);
+          if (WINDOW) {
+            const long long fx = __float2ll_rn(d * 1099511627776.0f);  // 2^40
+            const uint32_t lo = (uint32_t)fx;
+            uint32_t* slot = dtab_s + 2 * ((int)(qinf[r] & 0xffffu) - (int)(kw & 0xffffu));
+            const uint32_t old = atomicAdd(slot, lo);
+            atomicAdd(slot + 1, (uint32_t)(fx >> 32) + ((old + lo) < old ? 1u : 0u));
+          }
+          ds[e] = d * sc;
+        }
+        dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
+        dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
       }
-      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
-      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; dt += 2) {
+          uint32_t b[4];
+          ldsm_x4_t(b, s_u32(Ks + ((hh * 2 + kk) * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+          mma16816(dq[dt], dsf[kk], b);
+          mma16816(dq[dt + 1], dsf[kk], b + 2);
+        }
     }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int dt = 0; dt < HD / 8; dt += 2) {
-        uint32_t b[4];
-        ldsm_x4_t(b, s_u32(Ks + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-        mma16816(dq[dt], dsf[kk], b);
-        mma16816(dq[dt + 1], dsf[kk], b + 2);
-      }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -487,14 +498,14 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   if (WINDOW && P.dtable != nullptr) {
     __syncthreads();
     for (int r = threadIdx.x; r < n_rel; r += blockDim.x) {
-      const float v = dtab_s[r];
-      if (v != 0.f) atomicAdd(&P.dtable[(size_t)r * P.win.heads + h], v);
+      const long long v = (long long)(((unsigned long long)dtab_s[2 * r + 1] << 32) | dtab_s[2 * r]);
+      if (v != 0) atomicAdd(&P.dtable[(size_t)r * P.win.heads + h], (float)((double)v * (1.0 / 1099511627776.0)));
     }
   }
 }
 
 template <int HD, bool WINDOW>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pad, int nk_pad) {
   constexpr int PITCH = HD * 2 + 16, TILE = 64 * PITCH;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -551,57 +562,60 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
       load_tile_async<HD>(Qn + TILE, P.dO, P.ldo, col0, t.qrow_s, (qb + 1) * BQ);
       cp_async_commit();
     }
-    float s[8][4], dp[8][4];  // rows = keys (g, g+8), cols = queries of this block
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {  // two 32-query halves
+      float s[4][4], dp[4][4];  // rows = keys (g, g+8), cols = queries
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
+        for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks)
+      for (int ks = 0; ks < HD / 16; ++ks)
 #pragma unroll
-      for (int nt = 0; nt < 8; nt += 2) {
-        uint32_t b[4];
-        ldsm_x4(b, s_u32(Qs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-        mma16816(s[nt], kf[ks], b);
-        mma16816(s[nt + 1], kf[ks], b + 2);
-        ldsm_x4(b, s_u32(dOs + ((nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-        mma16816(dp[nt], vf[ks], b);
-        mma16816(dp[nt + 1], vf[ks], b + 2);
+        for (int nt = 0; nt < 4; nt += 2) {
+          uint32_t b[4];
+          ldsm_x4(b, s_u32(Qs + ((hh * 4 + nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+          mma16816(s[nt], kf[ks], b);
+          mma16816(s[nt + 1], kf[ks], b + 2);
+          ldsm_x4(b, s_u32(dOs + ((hh * 4 + nt + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
+          mma16816(dp[nt], vf[ks], b);
+          mma16816(dp[nt + 1], vf[ks], b + 2);
+        }
+      uint32_t pf[2][4], dsf[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int ib = qb * BQ + (hh * 4 + nt) * 8 + t4 * 2;   // two consecutive queries (columns of S^T)
+        const uint2 qi2 = lds_v2u32(t.qinfo_s + 4u * (uint32_t)ib);
+        const float2 l2 = *(const float2*)(lse_s + ib);
+        const float2 d2 = *(const float2*)(del_s + ib);
+        float pv[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const uint32_t qw = (e & 1) ? qi2.y : qi2.x;
+          const float v = score2<WINDOW>(t, s[nt][e], sc2, qw, kinf[r], ib + (e & 1), j0 + r * 8);
+          const float pr = fast_exp2(v - ((e & 1) ? l2.y : l2.x));   // padding queries carry lse = +inf -> 0
+          pv[e] = pr;
+          ds[e] = pr * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * sc;
+        }
+        pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+        dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
+        dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
       }
-    uint32_t pf[4][4], dsf[4][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int ib = qb * BQ + nt * 8 + t4 * 2;   // two consecutive queries (columns of S^T)
-      const uint2 qi2 = lds_v2u32(t.qinfo_s + 4u * (uint32_t)ib);
-      const float2 l2 = *(const float2*)(lse_s + ib);
-      const float2 d2 = *(const float2*)(del_s + ib);
-      float pv[4], ds[4];
+      for (int kk = 0; kk < 2; ++kk)  // contraction over the 32 queries of this half
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = e >> 1;
-        const uint32_t qw = (e & 1) ? qi2.y : qi2.x;
-        const float v = score2<WINDOW>(t, s[nt][e], sc2, qw, kinf[r], ib + (e & 1), j0 + r * 8);
-        const float pr = fast_exp2(v - ((e & 1) ? l2.y : l2.x));   // padding queries carry lse = +inf -> 0
-        pv[e] = pr;
-        ds[e] = pr * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * sc;
-      }
-      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
-      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
-      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        for (int dt = 0; dt < HD / 8; dt += 2) {
+          uint32_t b[4];
+          ldsm_x4_t(b, s_u32(dOs + ((hh * 2 + kk) * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+          mma16816(dv[dt], pf[kk], b);
+          mma16816(dv[dt + 1], pf[kk], b + 2);
+          ldsm_x4_t(b, s_u32(Qs + ((hh * 2 + kk) * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
+          mma16816(dk[dt], dsf[kk], b);
+          mma16816(dk[dt + 1], dsf[kk], b + 2);
+        }
     }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)  // contraction over the 64 queries of the block
-#pragma unroll
-      for (int dt = 0; dt < HD / 8; dt += 2) {
-        uint32_t b[4];
-        ldsm_x4_t(b, s_u32(dOs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-        mma16816(dv[dt], pf[kk], b);
-        mma16816(dv[dt + 1], pf[kk], b + 2);
-        ldsm_x4_t(b, s_u32(Qs + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-        mma16816(dk[dt], dsf[kk], b);
-        mma16816(dk[dt + 1], dsf[kk], b + 2);
-      }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -661,7 +675,7 @@ static int launch_bwd(const AttnParams& P, float* delta, int Pn, int nq, int max
   if (WINDOW) n_rel = (size_t)(2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
   const size_t tb = table_bytes<HD, WINDOW>(P, nq_pad, nk_pad);
   {
-    const size_t smem = 6 * 64 * PITCH + sizeof(float) * (128 + n_rel) + tb + 32;
+    const size_t smem = 6 * 64 * PITCH + sizeof(float) * (128 + 2 * n_rel) + tb + 32;
     auto kern = attn_mma_bwd_dq_kernel<HD, WINDOW>;
     if (smem > 48 * 1024) VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nq_pad / 64, Pn, P.H);
