@@ -85,8 +85,10 @@ int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm,
  * starting at kv_row0[p] (NULL: p*max_nk) of K/V; head h occupies columns [h*hd,(h+1)*hd).
  * scores = q.k^T * scale + mask, mask = -10000 where key_valid[p,j]==0 or (causal[p] && j>i)
  * (bert.py:869-885).  lse [P,H,Nq] fp32 is saved for the backward.
- * Backward: dQ written; dK/dV accumulated with += into fp32 [rows, H*hd] buffers the caller
- * zero-fills (K/V rows shared by several problems add up); `delta` is a [P,H,Nq] fp32 scratch
+ * Backward: dQ written.  dK/dV either accumulate (+=) into fp32 [rows, H*hd] buffers the caller zero-fills
+ * (dK/dV: K/V rows shared by several problems add up — cross-attention), or, when every K/V row belongs to
+ * exactly one problem (self-attention), are written directly in the compute dtype to dK_lp/dV_lp (pitch
+ * lddkv_lp); exactly one of the two output pairs is non-NULL.  `delta` is a [P,H,Nq] fp32 scratch
  * (rowsum(dO*O), produced by the dQ kernel and consumed by the dK/dV kernel). */
 int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
                   void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
@@ -94,9 +96,10 @@ int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long l
                   float scale, int backend, void* stream);
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                   long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta,
-                  void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd,
-                  int Nq, int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
-                  const unsigned char* key_valid, const unsigned char* causal, float scale, int backend, void* stream);
+                  void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp,
+                  void* dV_lp, long long lddkv_lp, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
+                  const int* kv_row0, const int* kv_len, const unsigned char* key_valid,
+                  const unsigned char* causal, float scale, int backend, void* stream);
 
 /* ---- VideoSwin shifted-window attention: WindowAttention3D.forward (videoswin.py:137-163)
  * together with torch.roll / window_partition / window_reverse / compute_mask

@@ -131,7 +131,7 @@ def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv
 
 
 def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
-            key_valid=None, causal=None, backend=0):
+            key_valid=None, causal=None, dkv_out=None, backend=0):
     dkv = torch.zeros(k.shape[0], 2 * H * hd)
     for p in range(P_):
         q0, k0, nk = _mha_problem(p, Nq, max_nk, q_row0, kv_row0, kv_len)
@@ -146,6 +146,10 @@ def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=No
             dq_out[q0:q0 + Nq, sl] = (ds @ kk).to(dq_out.dtype)
             dkv[k0:k0 + nk, sl] += ds.t() @ qq
             dkv[k0:k0 + nk, H * hd + h * hd:H * hd + (h + 1) * hd] += pr.t() @ dd
+    if dkv_out is not None:
+        dkv_out[0].copy_(dkv[:, :H * hd].to(dkv_out[0].dtype))
+        dkv_out[1].copy_(dkv[:, H * hd:].to(dkv_out[1].dtype))
+        return None
     return dkv
 
 

@@ -217,6 +217,10 @@ def test_mha(dtype, case):
     dkv = k.mha_bwd(qd, kd, vd, o, dev(do, dtype), lse, dq, P_, H, hd, Nq, nk, scale, **kwd)
     close(dq, dq_r, dtype, "mha dq")
     close(dkv, dkv_r, dtype, "mha dkv")
+    if case != "cross":  # self-attention: every K/V row has one owner -> direct outputs in the compute dtype
+        dkv2 = torch.full((P_ * Nq, 2 * Hd), 7.0, device="cuda", dtype=dtype)
+        k.mha_bwd(qd, kd, vd, o, dev(do, dtype), lse, dq, P_, H, hd, Nq, nk, scale, dkv_out=(dkv2[:, :Hd], dkv2[:, Hd:]), **kwd)
+        close(dkv2, dkv_r, dtype, "mha dkv direct")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -65,8 +65,8 @@ int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V,
                 long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
 int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                 long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta, void* dQ,
-                long long lddq, float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq,
-                float scale, cudaStream_t st);
+                long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp, void* dV_lp,
+                long long lddkv_lp, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
 int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
                    int H, int hd, float scale, cudaStream_t st);
 int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
@@ -145,16 +145,23 @@ int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long l
 }
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                   long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta,
-                  void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, int P, int H, int hd,
-                  int Nq, int max_nk, const int* q_row0, const int* kv_row0, const int* kv_len,
-                  const unsigned char* key_valid, const unsigned char* causal, float scale, int backend, void* stream) {
+                  void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp,
+                  void* dV_lp, long long lddkv_lp, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
+                  const int* kv_row0, const int* kv_len, const unsigned char* key_valid,
+                  const unsigned char* causal, float scale, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
   const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O) && (lddq % 8 == 0) &&
                   (((uintptr_t)dQ | (uintptr_t)dO) & 15) == 0 && delta != nullptr;
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_bwd: tensor backend requested but not eligible");
   if (backend != VALOR_BACKEND_SIMT && ok)
-    return mha_mma_bwd(ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, delta, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq, scale, ST);
+    return mha_mma_bwd(ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, delta, dQ, lddq, dK, dV, lddk, lddv, dK_lp, dV_lp,
+                       lddkv_lp, P, H, hd, Nq, scale, ST);
+  // row-per-warp path: fp32 accumulation only; in fp32 parity mode the "direct" outputs ARE fp32 buffers
+  if (dK == nullptr && dtype == VALOR_DT_F32 && dK_lp != nullptr) {
+    dK = (float*)dK_lp; dV = (float*)dV_lp; lddk = lddv = lddkv_lp;
+  }
+  VALOR_REQUIRE(dK != nullptr && dV != nullptr, "valor_mha_bwd: SIMT path needs fp32 dK/dV accumulators");
   return mha_ref_bwd(dtype, ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, dQ, lddq, dK, dV, lddk, lddv, P, H, hd, Nq,
                      scale, ST);
 }

@@ -713,12 +713,14 @@ int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V,
 
 int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                 long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta, void* dQ,
-                long long lddq, float* dK, float* dV, long long lddk, long long lddv, int Pn, int H, int hd, int Nq,
-                float scale, cudaStream_t st) {
+                long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp, void* dV_lp,
+                long long lddkv_lp, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st) {
   AttnParams P = {};
   P.Q = (const bf16*)Q; P.K = (const bf16*)K; P.V = (const bf16*)V; P.ldq = ldq; P.ldk = ldk; P.ldv = ldv;
   P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.H = H; P.hd = hd; P.Nq = Nq; P.max_nk = ix.max_nk; P.scale = scale;
   P.dO = (const bf16*)dO; P.dQ = (bf16*)dQ; P.lddq = lddq; P.dK = dK; P.dV = dV; P.lddk = lddk; P.lddv = lddv;
+  P.dK_lp = (bf16*)dK_lp; P.dV_lp = (bf16*)dV_lp; P.lddkv_lp = lddkv_lp;
+  VALOR_REQUIRE((dK != nullptr) != (dK_lp != nullptr), "mha_bwd: give exactly one of (dK,dV) / (dK_lp,dV_lp)");
   P.mha = ix;
   VALOR_REQUIRE(Pn <= 65535 && H <= 65535, "mha: too many problems/heads");
   return hd == 32 ? launch_bwd<32, false>(P, delta, Pn, Nq, ix.max_nk, st)

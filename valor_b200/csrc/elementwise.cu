@@ -222,22 +222,24 @@ __global__ void media_input_fwd_kernel(const T* __restrict__ in, const float* __
   }
 }
 // din = dout slice; dframe[f] += sum_{b,x}; dtype += sum_{b,f,x}
+// grid (nf, B-chunks): each CTA walks its (b-chunk, f) rows with all threads across Hd (coalesced), keeps the
+// column sums in registers and issues one atomicAdd per column.
 template <typename T>
-__global__ void media_input_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din, float* __restrict__ dframe,
-                                       float* __restrict__ dtype, int B, int nf, int X, int Hd, int S_total, int row0) {
-  const long long total = (long long)nf * Hd;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % Hd);
-    const int f = (int)(idx / Hd);
+__global__ void __launch_bounds__(256)
+media_input_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din, float* __restrict__ dframe,
+                       float* __restrict__ dtype, int B, int nf, int X, int Hd, int S_total, int row0, int b_per) {
+  const int f = blockIdx.x;
+  const int b0 = blockIdx.y * b_per;
+  const int b1 = min(B, b0 + b_per);
+  for (int c = threadIdx.x; c < Hd; c += blockDim.x) {
     float s = 0.f;
-    for (long long b = 0; b < B; ++b)
+    for (int b = b0; b < b1; ++b)
       for (int x = 0; x < X; ++x) {
-        const T v = dout[(b * S_total + row0 + f * X + x) * Hd + c];
+        const T v = dout[((long long)b * S_total + row0 + f * X + x) * Hd + c];
         s += to_f(v);
-        din[((b * nf + f) * X + x) * Hd + c] = v;
+        din[(((long long)b * nf + f) * X + x) * Hd + c] = v;
       }
-    if (dframe) atomicAdd(&dframe[idx], s);
+    if (dframe) atomicAdd(&dframe[(long long)f * Hd + c], s);
     if (dtype) atomicAdd(&dtype[c], s);
   }
 }
@@ -250,9 +252,10 @@ int media_input_fwd(int dtype, const void* in, const float* frame_emb, const flo
 }
 int media_input_bwd(int dtype, const void* dout, void* din, float* dframe, float* dtype_emb, int B, int nf, int X,
                     int Hd, int S_total, int row0, cudaStream_t st) {
-  unsigned g = grid_for((long long)nf * Hd, 64);
-  if (dtype == VALOR_DT_F32) media_input_bwd_kernel<float><<<g, 64, 0, st>>>((const float*)dout, (float*)din, dframe, dtype_emb, B, nf, X, Hd, S_total, row0);
-  else media_input_bwd_kernel<bf16><<<g, 64, 0, st>>>((const bf16*)dout, (bf16*)din, dframe, dtype_emb, B, nf, X, Hd, S_total, row0);
+  const int b_per = B >= 64 ? 4 : (B >= 16 ? 2 : 1);
+  dim3 g(nf, (B + b_per - 1) / b_per);
+  if (dtype == VALOR_DT_F32) media_input_bwd_kernel<float><<<g, 256, 0, st>>>((const float*)dout, (float*)din, dframe, dtype_emb, B, nf, X, Hd, S_total, row0, b_per);
+  else media_input_bwd_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)dout, (bf16*)din, dframe, dtype_emb, B, nf, X, Hd, S_total, row0, b_per);
   return check_launch("media_input_bwd_kernel");
 }
 

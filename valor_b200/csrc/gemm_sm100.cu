@@ -103,7 +103,8 @@ enum EpiMode { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES = 2, EPI_GELU_PRE = 3, EP
 // One 32-column slab of one accumulator row: v (raw TMEM words) -> staging row(s) in shared memory.
 template <int MODE>
 __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, const GemmEpilogue& ep, int row, int col0, int M,
-                                         int N, int lane, int sub, uint8_t* st_out, uint8_t* st_pre) {
+                                         int N, int lane, int sub, uint8_t* st_out, uint8_t* st_pre,
+                                         const uint8_t* in_tile) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float xg[8];
@@ -122,8 +123,17 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
       *(uint4*)(st_pre + soff) = pk;
     }
     const bool use_aux = (MODE == EPI_GELU_AUX) || (MODE == EPI_GENERIC && ep.act_aux != nullptr);
-    if (use_aux) {
-      const int act = (MODE == EPI_GELU_AUX) ? VALOR_ACT_GELU : ep.act;
+    if (MODE == EPI_GELU_AUX) {   // aux tile staged in shared memory by TMA (same 128B swizzle as the output)
+      const uint4 a = *(const uint4*)(in_tile + soff);
+      const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        xg[2 * j] *= act_grad(f.x, VALOR_ACT_GELU);
+        xg[2 * j + 1] *= act_grad(f.y, VALOR_ACT_GELU);
+      }
+    } else if (use_aux) {
+      const int act = ep.act;
       if (inb) {
         uint4 a = *(const uint4*)((const bf16*)ep.act_aux + (size_t)row * ep.ld_aux + col);
         const __nv_bfloat162* h = (const __nv_bfloat162*)&a;
@@ -146,8 +156,17 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
         for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], ep.act);
       }
     }
-    const bool use_res = (MODE == EPI_RES) || (MODE == EPI_GENERIC && ep.residual != nullptr);
-    if (use_res) {
+    const bool use_res = (MODE == EPI_GENERIC && ep.residual != nullptr);
+    if (MODE == EPI_RES) {        // residual tile staged in shared memory by TMA
+      const uint4 r = *(const uint4*)(in_tile + soff);
+      const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        xg[2 * j] += f.x;
+        xg[2 * j + 1] += f.y;
+      }
+    } else if (use_res) {
       if (inb) {
         uint4 r = *(const uint4*)((const bf16*)ep.residual + (size_t)row * ep.ldr + col);
         const __nv_bfloat162* h = (const __nv_bfloat162*)&r;
@@ -226,6 +245,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[2 * STAGES + 6 + i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -326,6 +346,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // bias slice and issues its own bulk stores: no CTA-level barrier anywhere in the epilogue.
     uint8_t* wst = staging + e * 8192;
     float* wbias = bias_s + e * 128;
+    // RES / GELU_AUX: the residual / saved pre-activation tile of each chunk arrives by TMA into the warp's
+    // second staging buffer (coalesced 128-byte rows instead of 32 row-strided 16-byte loads per instruction)
+    constexpr bool kInTile = (MODE == EPI_RES) || (MODE == EPI_GELU_AUX);
+    uint64_t* in_bar = bars + 2 * STAGES + 6 + e;
+    uint32_t in_phase = 0;
     const bool has_pre = ep.preact_out != nullptr;
     uint32_t chunk_ctr = 0;
     int acc = 0;
@@ -364,6 +389,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           wbias[cc * 64 + 32 + lane] = (ep.bias != nullptr && cb + 32 < N) ? ep.bias[cb + 32] : 0.f;
         }
         __syncwarp();
+        if (kInTile && lane == 0 && n0 + half * 64 < N) {   // first chunk's input tile, in flight while the MMAs finish
+          mbar_expect_tx(in_bar, 4096);
+          tma_load_2d(&tmP, in_bar, wst + 4096, n0 + half * 64, m_blk * BLOCK_M + q * 32);
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tcgen05_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
@@ -377,22 +406,31 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (n0 + c * 64 >= N) break;
           // staging: [out | pre] when the pre-activation side output exists (single-buffered), otherwise the
           // two buffers alternate so the TMA store of chunk i overlaps the TMEM reads / math of chunk i+1
-          uint8_t* st_out = wst + ((!has_pre && (chunk_ctr & 1)) ? 4096 : 0);
+          const bool single = has_pre || kInTile;   // second buffer taken by the side output / the input tile
+          uint8_t* st_out = wst + ((!single && (chunk_ctr & 1)) ? 4096 : 0);
           uint8_t* st_pre = wst + 4096;
           ++chunk_ctr;
           if (lane == 0) {
-            if (has_pre) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (single) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
           tmem_ld_wait();
           __syncwarp();
+          if (kInTile) {
+            mbar_wait(in_bar, in_phase);
+            in_phase ^= 1;
+          }
           const bool more = (c + 2 < BLOCK_N / 64) && (n0 + (c + 2) * 64 < N);
-          epi_slab<MODE>(va, wbias + cc * 64, ep, row, n0 + c * 64, M, N, lane, 0, st_out, st_pre);
+          epi_slab<MODE>(va, wbias + cc * 64, ep, row, n0 + c * 64, M, N, lane, 0, st_out, st_pre, st_pre);
           if (more) tmem_ld_32x32(trow + (c + 2) * 64, va);       // next chunk's slabs stream in while this one
-          epi_slab<MODE>(vb, wbias + cc * 64 + 32, ep, row, n0 + c * 64 + 32, M, N, lane, 1, st_out, st_pre);
+          epi_slab<MODE>(vb, wbias + cc * 64 + 32, ep, row, n0 + c * 64 + 32, M, N, lane, 1, st_out, st_pre, st_pre);
           if (more) tmem_ld_32x32(trow + (c + 2) * 64 + 32, vb);  // is converted, staged and stored
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
+          if (kInTile && more && lane == 0) {   // every lane has consumed the input tile: fetch the next one
+            mbar_expect_tx(in_bar, 4096);
+            tma_load_2d(&tmP, in_bar, st_pre, n0 + (c + 2) * 64, m_blk * BLOCK_M + q * 32);
+          }
           if (lane == 0 && !(dbg & 2)) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              (uint64_t)&tmC),
@@ -634,6 +672,8 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   int mode = EPI_GENERIC;
   if (tma_store) {
     const bool res = ep.residual != nullptr, aux = ep.act_aux != nullptr, pre = ep.preact_out != nullptr;
+    if (res && !aux && !pre && ep.act == VALOR_ACT_NONE) { if (make_tmap(&tp, ep.residual, N, M, ep.ldr, 32)) return 1; }
+    if (!res && aux && !pre && ep.act == VALOR_ACT_GELU && ep.bias == nullptr) { if (make_tmap(&tp, ep.act_aux, N, M, ep.ld_aux, 32)) return 1; }
     if (!res && !aux && !pre && ep.act == VALOR_ACT_NONE) mode = EPI_PLAIN;
     else if (res && !aux && !pre && ep.act == VALOR_ACT_NONE) mode = EPI_RES;
     else if (!res && !aux && pre && ep.act == VALOR_ACT_GELU) mode = EPI_GELU_PRE;

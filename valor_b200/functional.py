@@ -216,9 +216,9 @@ class SelfAttnFn(Function):
         s = ctx.spec
         Hd = s["H"] * s["hd"]
         dqkv = torch.empty_like(qkv)
-        dkv = K.mha_bwd(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], o, do, lse, dqkv[:, :Hd], s["P"], s["H"],
-                        s["hd"], s["Nq"], s["max_nk"], s["scale"], key_valid=s.get("key_valid"), causal=s.get("causal"))
-        K.cast2d(dkv, dqkv[:, Hd:])
+        K.mha_bwd(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], o, do, lse, dqkv[:, :Hd], s["P"], s["H"], s["hd"],
+                  s["Nq"], s["max_nk"], s["scale"], key_valid=s.get("key_valid"), causal=s.get("causal"),
+                  dkv_out=(dqkv[:, Hd:2 * Hd], dqkv[:, 2 * Hd:]))
         return dqkv, None
 
 

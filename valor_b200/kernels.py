@@ -136,15 +136,26 @@ def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv
 
 
 def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
-            key_valid=None, causal=None, backend=BACKEND_AUTO):
-    """dq_out: [rows_q, >=H*hd] view receiving dQ; returns fp32 (dK, dV) [rows_kv, H*hd] (accumulated)."""
-    dkv = torch.zeros(k.shape[0], 2 * H * hd, device=q.device, dtype=torch.float32)
-    dk, dv = dkv[:, : H * hd], dkv[:, H * hd:]
+            key_valid=None, causal=None, dkv_out=None, backend=BACKEND_AUTO):
+    """dq_out: [rows_q, >=H*hd] view receiving dQ.
+    dkv_out=None  -> returns an fp32 [rows_kv, 2*H*hd] buffer with dK|dV accumulated (shared K/V rows: cross-attention);
+    dkv_out=(dk_view, dv_view) in the compute dtype -> written directly (each K/V row owned by one problem)."""
     do = do.contiguous()
     delta = torch.empty_like(lse)
+    if dkv_out is None:
+        dkv = torch.zeros(k.shape[0], 2 * H * hd, device=q.device, dtype=torch.float32)
+        dk, dv = dkv[:, : H * hd], dkv[:, H * hd:]
+        args = (P(dk), P(dv), _ld(dk), _ld(dv), None, None, 0)
+    else:
+        dkv = None
+        dk, dv = dkv_out
+        if q.dtype == torch.float32:   # parity mode: the row kernel accumulates -> needs zeros
+            dk.zero_()
+            dv.zero_()
+        args = (None, None, 0, 0, P(dk), P(dv), _ld(dk))
     _call("valor_mha_bwd", DT(q), P(q), P(k), P(v), P(o), P(do), _ld(q), _ld(k), _ld(v), _ld(o), P(lse), P(delta), P(dq_out),
-          _ld(dq_out), P(dk), P(dv), _ld(dk), _ld(dv), P_, H, hd, Nq, max_nk, P(q_row0), P(kv_row0), P(kv_len),
-          P(key_valid), P(causal), float(scale), backend, ST())
+          _ld(dq_out), *args, P_, H, hd, Nq, max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal),
+          float(scale), backend, ST())
     return dkv
 
 
