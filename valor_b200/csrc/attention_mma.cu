@@ -357,9 +357,9 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   float* del_s = lse_s + 64;                 // [64]
   // window: bias-table gradient in shared memory.  Only 32-bit INTEGER shared atomics are native (fp32 and
   // 64-bit ones compile to compare-and-swap spin loops, which dominated this kernel), so each slot is a
-  // 64-bit two's-complement fixed-point sum (scale 2^40) kept as two words: ATOMS.ADD on the low word returns
-  // the old value, the carry is folded into the ATOMS.ADD on the high word.  Integer adds commute: the result
-  // is exact and order-independent.
+  // pair of int32 fixed-point words: a coarse word in units of 2^-16 (|per-CTA sum| < 32768) and the rounding
+  // remainder in units of 2^-40 (64 contributions of < 2^23 each never overflow).  Two ATOMS.ADD without
+  // return per element; integer adds commute, so the result is order-independent.
   uint32_t* dtab_s = (uint32_t*)(del_s + 64);  // [n_rel][2] : lo, hi words of a 64-bit fixed-point sum
   const int p = blockIdx.y, h = blockIdx.z, qb = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
@@ -463,11 +463,12 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
           if (ragged && (kw >> 31)) pr = 0.f;
           const float d = pr * (dp[nt][e] - del[r]);
           if (WINDOW) {
-            const long long fx = __float2ll_rn(d * 1099511627776.0f);  // 2^40
-            const uint32_t lo = (uint32_t)fx;
-            uint32_t* slot = dtab_s + 2 * ((int)(qinf[r] & 0xffffu) - (int)(kw & 0xffffu));
-            const uint32_t old = atomicAdd(slot, lo);
-            atomicAdd(slot + 1, (uint32_t)(fx >> 32) + ((old + lo) < old ? 1u : 0u));
+            // two native int32 adds without return: coarse word at 2^-16, remainder word at 2^-40
+            const int hi = __float2int_rn(d * 65536.0f);
+            const int lo = __float2int_rn(fmaf((float)hi, -1.0f / 65536.0f, d) * 1099511627776.0f);
+            int* slot = (int*)dtab_s + 2 * ((int)(qinf[r] & 0xffffu) - (int)(kw & 0xffffu));
+            atomicAdd(slot, lo);
+            atomicAdd(slot + 1, hi);
           }
           ds[e] = d * sc;
         }
@@ -498,8 +499,9 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   if (WINDOW && P.dtable != nullptr) {
     __syncthreads();
     for (int r = threadIdx.x; r < n_rel; r += blockDim.x) {
-      const long long v = (long long)(((unsigned long long)dtab_s[2 * r + 1] << 32) | dtab_s[2 * r]);
-      if (v != 0) atomicAdd(&P.dtable[(size_t)r * P.win.heads + h], (float)((double)v * (1.0 / 1099511627776.0)));
+      const int lo = (int)dtab_s[2 * r], hi = (int)dtab_s[2 * r + 1];
+      if (lo != 0 || hi != 0)
+        atomicAdd(&P.dtable[(size_t)r * P.win.heads + h], (float)hi * (1.0f / 65536.0f) + (float)lo * (1.0f / 1099511627776.0f));
     }
   }
 }
