@@ -233,9 +233,11 @@ def test_mha(dtype, case):
 ])
 def test_window_attention(dtype, grid, win, shift, heads):
     """shift / partition / relative-position bias / -100 mask evaluated in-kernel vs the reference's
-    roll + window_partition + bias gather + compute_mask (videoswin.py:75-84,137-163,272-285)."""
+    roll + window_partition + bias gather + compute_mask (videoswin.py:75-84,137-163,272-285).
+    heads == 2 cases run head dim 64 (the key-blocked flash kernels), the others head dim 32
+    (the one-CTA-per-window kernels)."""
     k = K()
-    hd = 32
+    hd = 64 if (heads == 2 and grid[1] == 16) else 32
     C = heads * hd
     cfg_win = (8, 7, 7)
     tokens = grid[0] * grid[1] * grid[2] * grid[3]

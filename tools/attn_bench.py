@@ -24,22 +24,22 @@ def bench(fn, iters=5):
 
 
 def window(B, grid_hw, heads, shift, name):
-    D, H, W = 8, grid_hw, grid_hw
+    D, H, W = 4, grid_hw, grid_hw   # C2: 8 frames -> 4 temporal tokens, effective window (4,7,7)
     hd, C = 32, heads * 32
     tokens = B * D * H * W
     qkv = torch.randn(tokens, 3 * C, device="cuda", dtype=torch.bfloat16)
     table = torch.randn(15 * 13 * 13, heads, device="cuda") * 0.5
     do = torch.randn(tokens, C, device="cuda", dtype=torch.bfloat16)
-    geom = ((B, D, H, W), (8, 7, 7), shift, (8, 7, 7), heads, hd, hd ** -0.5)
+    geom = ((B, D, H, W), (4, 7, 7), shift, (8, 7, 7), heads, hd, hd ** -0.5)
     o, lse = K.window_attn_fwd(qkv, table, *geom)
     dt = torch.zeros_like(table)
     ms_f = bench(lambda: K.window_attn_fwd(qkv, table, *geom))
     ms_b = bench(lambda: K.window_attn_bwd(qkv, o, do, lse, table, dt, *geom))
     nprob = B * (H // 7) * (W // 7) * heads
-    fl = 4.0 * 392 * 392 * hd * nprob
+    fl = 4.0 * 196 * 196 * hd * nprob
     print(json.dumps({"kernel": name, "problems": nprob, "fwd_ms": round(ms_f, 3), "bwd_ms": round(ms_b, 3),
                       "fwd_tflops": round(fl / ms_f / 1e9, 1), "bwd_tflops": round(2.5 * fl / ms_b / 1e9, 1),
-                      "elems_per_ns_fwd": round(392 * 392 * nprob / ms_f / 1e6, 1)}), flush=True)
+                      "elems_per_ns_fwd": round(196 * 196 * nprob / ms_f / 1e6, 1)}), flush=True)
 
 
 def main():

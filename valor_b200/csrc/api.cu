@@ -73,9 +73,22 @@ int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const v
                    const float* lse, float* delta, void* dqkv, long long lddq, float* dtable, int Pn, int H, int hd,
                    float scale, cudaStream_t st);
 
+bool window_cta_eligible(const WindowIndex& ix, int hd);
+int window_cta_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
+                   int H, int hd, float scale, cudaStream_t st);
+int window_cta_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
+                   const float* lse, void* dqkv, long long lddqkv, float* dtable, int Pn, int H, int hd, float scale,
+                   cudaStream_t st);
+
 }  // namespace valor
 
 using namespace valor;
+// VALOR_WINDOW_FLASH=1 keeps window attention on the key-blocked flash kernels (A/B measurements)
+static bool window_use_cta(const WindowIndex& ix, int hd) {
+  static int flash = -1;
+  if (flash < 0) { const char* e = getenv("VALOR_WINDOW_FLASH"); flash = e ? atoi(e) : 0; }
+  return !flash && window_cta_eligible(ix, hd);
+}
 #define ST ((cudaStream_t)stream)
 
 extern "C" {
@@ -189,6 +202,8 @@ int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, lon
   const char* qb = (const char*)qkv;
   const bool ok = attn_mma_eligible(dtype, hd, ld, ld, ld, ldo, qb, qb + 2 * heads * hd, qb + 4 * heads * hd, O);
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_window_attn_fwd: tensor backend requested but not eligible");
+  if (backend != VALOR_BACKEND_SIMT && ok && window_use_cta(ix, hd))
+    return window_cta_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
   if (backend != VALOR_BACKEND_SIMT && ok) return window_mma_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
   return window_ref_fwd(dtype, ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
 }
@@ -208,6 +223,9 @@ int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* 
   const int P = B * (D / wd) * (H / wh) * (W / ww);
   const int C = heads * hd;
   const long long tokens = (long long)B * D * H * W;
+  if (window_bwd_tensor_ok(dtype, hd, ld, backend) && lddqkv % 8 == 0 && ldo % 8 == 0 &&
+      ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) && window_use_cta(ix, hd))
+    return window_cta_bwd(ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);
   if (window_bwd_tensor_ok(dtype, hd, ld, backend) && lddqkv % 8 == 0 && ldo % 8 == 0 &&
       ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) && delta != nullptr)
     return window_mma_bwd(ix, qkv, ld, O, dO, ldo, lse, delta, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);

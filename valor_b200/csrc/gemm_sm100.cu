@@ -98,7 +98,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 //   GELU_PRE : bias, pre-activation side output, erf-GELU
 //   GELU_AUX : * GELU'(aux)   (dgrad through the activation)
 //   GENERIC  : everything decided at run time (other activations, odd combinations)
-enum EpiMode { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES = 2, EPI_GELU_PRE = 3, EPI_GELU_AUX = 4 };
+//   ACC      : fp32 accumulate into global memory by TMA reduce-add (split-K weight gradients)
+enum EpiMode { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES = 2, EPI_GELU_PRE = 3, EPI_GELU_AUX = 4, EPI_ACC = 5 };
 
 // One 32-column slab of one accumulator row: v (raw TMEM words) -> staging row(s) in shared memory.
 template <int MODE>
@@ -266,8 +267,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n_blk = w % n_blocks;
         const int rest = w / n_blocks;
-        const int ks = rest % k_splits;
-        const int m_blk = rest / k_splits;
+        const int m_blk = rest % m_blocks;
+        const int ks = rest / m_blocks;
         const int kb0 = ks * kb_per;
         const int kb1 = min(kb0 + kb_per, kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -306,7 +307,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int rest = w / n_blocks;
-        const int ks = rest % k_splits;
+        const int ks = rest / m_blocks;
         const int kb0 = ks * kb_per;
         const int kb1 = min(kb0 + kb_per, kb_total);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -358,8 +359,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int n_blk = w % n_blocks;
       const int rest = w / n_blocks;
-      const int m_blk = rest / k_splits;
-      const int ks = rest % k_splits;
+      const int m_blk = rest % m_blocks;
+      const int ks = rest / m_blocks;
       const int n0 = n_blk * BLOCK_N;
       const int row = m_blk * BLOCK_M + r_tile;
       if (!tma_store) {
@@ -379,6 +380,42 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (dbg & 1) {
         // (diagnostic) mainloop only: release the accumulator without reading it
       } else if (tma_store) {
+        if (MODE == EPI_ACC) {
+          // ---------- fp32 tile += accumulator: 32x32 fp32 slabs staged in swizzled smem, folded into global
+          // memory by the TMA unit (cp.reduce.async.bulk .add): coalesced 128-byte reductions at L2, no
+          // per-thread atomics, OOB rows/columns clipped by the tensor map ----------
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+          uint32_t va[32];
+          if (n0 + half * 32 < N) tmem_ld_32x32(trow + half * 32, va);
+#pragma unroll 1
+          for (int c = half; c < BLOCK_N / 32; c += 2) {
+            if (n0 + c * 32 >= N) break;
+            uint8_t* st_out = wst + ((chunk_ctr & 1) ? 4096 : 0);
+            ++chunk_ctr;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            tmem_ld_wait();
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t soff = (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) << 4);
+              *(float4*)(st_out + soff) =
+                  make_float4(__uint_as_float(va[4 * g]) * ep.alpha, __uint_as_float(va[4 * g + 1]) * ep.alpha,
+                              __uint_as_float(va[4 * g + 2]) * ep.alpha, __uint_as_float(va[4 * g + 3]) * ep.alpha);
+            }
+            if ((c + 2 < BLOCK_N / 32) && (n0 + (c + 2) * 32 < N)) tmem_ld_32x32(trow + (c + 2) * 32, va);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               (uint64_t)&tmC),
+                           "r"(smem_u32(st_out)), "r"(n0 + c * 32), "r"(m_blk * BLOCK_M + q * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        } else {
         // ---------- bf16 output through swizzled smem staging + TMA store (coalesced, OOB-clipped) ----------
         // bias for all of this warp's chunks of the tile, fetched before the accumulator is ready
         __syncwarp();
@@ -443,6 +480,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+        }
         }
       } else {
         // ---------- direct stores (fp32 / split-K accumulate / unaligned outputs) ----------
@@ -562,6 +600,23 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
+// 2-D fp32 tensor for the reduce-add epilogue: box = {32 floats (128 B), 32 rows}, 128B swizzle.
+static int make_tmap_f32(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld) {
+  memset(tm, 0, sizeof(*tm));
+  auto fn = get_encode_fn();
+  VALOR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VALOR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed (%d): inner=%llu outer=%llu ld=%llu ptr=%p", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, ptr);
+  return 0;
+}
+
 template <int BN, bool AK, bool BK, int MODE>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, void* C,
                       long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
@@ -628,11 +683,18 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   if (force_splits > 0) {
     k_splits = force_splits;
   } else if (ep.accumulate && ep.out_dtype == VALOR_DT_F32) {
+    // split-K chosen to minimise the makespan of the persistent schedule: rounds of `sms` work items, each
+    // costing its k-blocks plus a fixed epilogue/drain term (in k-block units)
     const long tiles = (long)m_blocks * n_blocks;
-    if (tiles < sms) {
-      k_splits = (int)((2L * sms + tiles - 1) / tiles);
-      int max_splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
-      if (k_splits > max_splits) k_splits = max_splits;
+    const int max_splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+    const long epi_cost = 6;
+    long best_cost = -1;
+    for (int s = 1; s <= max_splits && s <= 512; ++s) {
+      const long per = (kb_total + s - 1) / s;
+      const long s_eff = (kb_total + per - 1) / per;
+      const long rounds = (tiles * s_eff + sms - 1) / sms;
+      const long cost = rounds * (per + epi_cost);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; k_splits = (int)s_eff; }
     }
   }
   if (k_splits > kb_total) k_splits = kb_total;
@@ -662,7 +724,16 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   CUtensorMap tc, tp;
   memset(&tc, 0, sizeof(tc));
   memset(&tp, 0, sizeof(tp));
-  if (tma_store) {
+  // fp32 accumulation (weight gradients) leaves through TMA reduce-add
+  static int no_acc_tma = -1;
+  if (no_acc_tma < 0) { const char* e = getenv("VALOR_GEMM_NO_TMA_REDUCE"); no_acc_tma = e ? atoi(e) : 0; }
+  const bool acc_tma = ep.accumulate && ep.out_dtype == VALOR_DT_F32 && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0) &&
+                       ep.bias == nullptr && ep.residual == nullptr && ep.act_aux == nullptr && ep.preact_out == nullptr &&
+                       ep.act == VALOR_ACT_NONE && !a_kmajor && !b_kmajor && !no_acc_tma;
+  if (acc_tma) {
+    tma_store = 1;
+    if (make_tmap_f32(&tc, C, N, M, ldc)) return 1;
+  } else if (tma_store) {
     if (make_tmap(&tc, C, N, M, ldc, 32)) return 1;
     if (ep.preact_out && make_tmap(&tp, ep.preact_out, N, M, ep.ld_pre, 32)) return 1;
   }
@@ -670,7 +741,9 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   const int grid = (int)(total < sms ? total : sms);
   // epilogue specialisation (TMA-store path only; everything else runs the generic code)
   int mode = EPI_GENERIC;
-  if (tma_store) {
+  if (acc_tma) {
+    mode = EPI_ACC;
+  } else if (tma_store) {
     const bool res = ep.residual != nullptr, aux = ep.act_aux != nullptr, pre = ep.preact_out != nullptr;
     if (res && !aux && !pre && ep.act == VALOR_ACT_NONE) { if (make_tmap(&tp, ep.residual, N, M, ep.ldr, 32)) return 1; }
     if (!res && aux && !pre && ep.act == VALOR_ACT_GELU && ep.bias == nullptr) { if (make_tmap(&tp, ep.act_aux, N, M, ep.ld_aux, 32)) return 1; }
@@ -697,6 +770,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     }
   }
   if (!a_kmajor && b_kmajor) VALOR_LAUNCH(false, true, EPI_GENERIC);
+  if (mode == EPI_ACC) VALOR_LAUNCH(false, false, EPI_ACC);
   VALOR_LAUNCH(false, false, EPI_GENERIC);
 #undef VALOR_LAUNCH
 }
