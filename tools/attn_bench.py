@@ -23,23 +23,24 @@ def bench(fn, iters=5):
     return e0.elapsed_time(e1) / iters
 
 
-def window(B, grid_hw, heads, shift, name):
-    D, H, W = 4, grid_hw, grid_hw   # C2: 8 frames -> 4 temporal tokens, effective window (4,7,7)
+def window(B, grid_hw, heads, shift, name, D=8):
+    H, W = grid_hw, grid_hw   # C2: 8 frames -> 8 temporal tokens (frames are embedded in pairs with themselves), window (8,7,7)
     hd, C = 32, heads * 32
     tokens = B * D * H * W
     qkv = torch.randn(tokens, 3 * C, device="cuda", dtype=torch.bfloat16)
     table = torch.randn(15 * 13 * 13, heads, device="cuda") * 0.5
     do = torch.randn(tokens, C, device="cuda", dtype=torch.bfloat16)
-    geom = ((B, D, H, W), (4, 7, 7), shift, (8, 7, 7), heads, hd, hd ** -0.5)
+    geom = ((B, D, H, W), (min(D, 8), 7, 7), shift, (8, 7, 7), heads, hd, hd ** -0.5)
+    N = min(D, 8) * 49
     o, lse = K.window_attn_fwd(qkv, table, *geom)
     dt = torch.zeros_like(table)
     ms_f = bench(lambda: K.window_attn_fwd(qkv, table, *geom))
     ms_b = bench(lambda: K.window_attn_bwd(qkv, o, do, lse, table, dt, *geom))
-    nprob = B * (H // 7) * (W // 7) * heads
-    fl = 4.0 * 196 * 196 * hd * nprob
+    nprob = B * (D // min(D, 8)) * (H // 7) * (W // 7) * heads
+    fl = 4.0 * N * N * hd * nprob
     print(json.dumps({"kernel": name, "problems": nprob, "fwd_ms": round(ms_f, 3), "bwd_ms": round(ms_b, 3),
                       "fwd_tflops": round(fl / ms_f / 1e9, 1), "bwd_tflops": round(2.5 * fl / ms_b / 1e9, 1),
-                      "elems_per_ns_fwd": round(196 * 196 * nprob / ms_f / 1e6, 1)}), flush=True)
+                      "elems_per_ns_fwd": round(N * N * nprob / ms_f / 1e6, 1)}), flush=True)
 
 
 def main():
@@ -50,6 +51,8 @@ def main():
         window(32, 56, 4, (0, 3, 3), "swin stage1 (shifted)")
     if "s3" in which:
         window(32, 14, 16, (0, 3, 3), "swin stage3 (shifted)")
+    if "d4" in which:
+        window(32, 56, 4, (0, 3, 3), "swin stage1, 4 temporal tokens (196-token windows)", D=4)
 
 
 if __name__ == "__main__":

@@ -1,26 +1,83 @@
 // valor_b200 — VideoSwin shifted-window attention, one CTA per (window, head).
 //
 // A 3-D window holds at most 8*7*7 = 392 tokens of 32 channels per head, so a whole attention
-// problem (Q, K, V and, backward, dO) fits in shared memory: 4 x 196 x 64 B = 50 KB for the
-// pre-training geometry.  The CTA builds the window's index / bias / mask tables ONCE, gathers the
-// token rows once (cyclic shift + window partition folded into the row index, videoswin.py:206-216),
-// and then every warp runs independently on its own 16-row blocks with no CTA barrier:
+// problem (Q, K, V and, backward, dO) fits in shared memory: 4 x 400 x 64 B = 100 KB.  The CTA
+// builds the window's index / bias / mask tables ONCE, gathers the token rows once (cyclic shift
+// and window partition folded into the row index, videoswin.py:206-216), and then every warp works
+// independently on 16-row blocks with no CTA barrier:
 //
-//   forward : warp owns 16 queries, sweeps all keys with an online softmax (S, P stay in registers)
-//   backward: units 0..nrb-1   = 16-query blocks -> dQ (and the relative-position-bias gradient),
-//             units nrb..2nrb-1 = 16-key blocks  -> dK, dV (S^T = K.Q^T so P^T / dS^T are produced
-//             directly in A-operand layout); units are dealt round-robin to the warps
+//   forward : a warp owns 16 queries and sweeps all keys with an online softmax; S and P stay in
+//             registers; the row sums come out of the P.V MMA through an all-ones extra column.
+//   backward: "dq warps" own 16-query blocks (dQ + relative-position-bias gradient), "dkv warps" own
+//             16-key blocks (S^T = K.Q^T so P^T / dS^T are born in A-operand layout; dK, dV).
 //
-// Relative-position bias (videoswin.py:113-127,150-153) and the -100 shift mask (videoswin.py:272-285)
-// are evaluated per score from one 32-bit info word per token; keys are enumerated (w,d,h) so the 32
-// lanes of an MMA fragment touch 32 distinct bias slots.  The bias gradient is accumulated in shared
-// memory with native 32-bit integer atomics (fp32 shared atomics are compare-and-swap loops) at a
-// per-CTA power-of-two scale derived from max|dO|.max|V|, then folded into the global fp32 table.
+// Relative-position bias (videoswin.py:113-127,150-153): per token one code word; the bias of a
+// pair is table[code_q - code_k].  Keys are enumerated (w,d,h) so the 32 lanes of an MMA fragment
+// read 32 distinct table slots.  The -100 shift mask (videoswin.py:272-285) only exists in windows
+// on the wrapped border of a shifted block; those CTAs run a MASKED instantiation, the others
+// never test it.
+//
+// Bias gradient: shared-memory atomics cost ~1 LSU cycle per LANE on this part and dominated the
+// backward pass.  Instead every dq warp owns a private fp32 copy of the table slice and folds its
+// dS tile in row by row with plain load / add / store: inside one query row all keys map to distinct
+// slots, so a warp-wide read-modify-write has no internal collision, and a warp's shared-memory
+// instructions retire in order.  The copies are summed and sent to the global table once per CTA.
 #include "common.cuh"
 #include "attention.cuh"
-#include "mma_utils.cuh"
+#include <algorithm>
 
 namespace valor {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kMask = -100.0f;   // videoswin.py:284
+
+// Shared-memory reads are volatile asm: they must stay behind the prologue barriers (a non-volatile asm without
+// a memory operand may legally be hoisted above __syncthreads); ptxas still schedules them freely.
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// d = a.b + c, accumulator in place
+__device__ __forceinline__ void mma_acc(float* c, const uint32_t* a, const uint32_t* b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// d = a.b + {c0, c1, c2, c3}: the initial accumulator comes from other registers (no separate moves)
+__device__ __forceinline__ void mma_init(float* d, const uint32_t* a, const uint32_t* b, float c0, float c1, float c2, float c3) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+__device__ __forceinline__ float ld_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 ld_v2u32(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float2 ld_v2f32(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Accesses to the warp-private read-modify-write regions (program order matters).
+__device__ __forceinline__ float ldv_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void stv_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void stv_v2f32(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y)); }
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// exact i / d for 0 <= i < 4096 and 1 <= d <= 256 (multiply-shift with a rounded-up reciprocal)
+__device__ __forceinline__ int small_div(int i, int inv) { return (int)(((unsigned)i * (unsigned)inv) >> 20); }
+__host__ __device__ __forceinline__ int small_inv(int d) { return (int)(((1u << 20) + d - 1) / d); }
 
 struct WinParams {
   const bf16* qkv; long long ld;   // [tokens, 3C]: Q | K | V
@@ -32,30 +89,28 @@ struct WinParams {
   float scale;
   int heads;
   int NP;                          // N rounded up to 16
-  int n_used, maxcode, center;     // bias slots reachable from this window: [center-maxcode, center+maxcode]
+  int n_used, maxcode, center;     // bias slots reachable inside one window: [center-maxcode, center+maxcode]
+  int tab_stride;                  // bytes between per-warp gradient tables (n_used*4 rounded up to 16)
+  int n_dq_warps;                  // backward: warps 0..n_dq_warps-1 take the query blocks, the rest the key blocks
   WindowIndex win;
 };
 
-template <int HD> struct WinCfg {
-  static constexpr int PITCH = HD * 2 + 16;  // bytes per staged row: 16-byte skew keeps ldmatrix conflict-free
-  static constexpr int CH = HD / 8;          // 16-byte chunks per row
+// Row tiles: 64 bytes per row (HD = 32 bf16), 16-byte chunk c of row r stored at chunk c ^ ((r >> 1) & 3): the 8 rows
+// of an ldmatrix phase then cover all 32 banks.
+constexpr int HD = 32;
+constexpr int ROWB = HD * 2;
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * ROWB + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+struct Smem {
+  unsigned char *Qs, *Ks, *Vs, *dOs;
+  int *qrow, *krow;
+  uint32_t *qcode, *kcode, *qreg, *kreg;
+  float* tab;
 };
 
-// exact i / d for 0 <= i < 4096, 1 <= d <= 4096 (multiply-shift with a rounded-up reciprocal)
-__device__ __forceinline__ int small_div(int i, int inv) { return (int)(((unsigned)i * (unsigned)inv) >> 20); }
-__host__ __device__ __forceinline__ int small_inv(int d) { return (int)(((1u << 20) + d - 1) / d); }
-
-struct WinTables {
-  uint32_t qrow_s, krow_s, qinfo_s, kinfo_s, tab2_s;  // shared-space addresses
-};
-
-// Per-token words:
-//   bits [0,16)  : byte offset into the CTA's bias slice (query: 4*(code+maxcode); key: 4*code)
-//   bits [16,24) : shift-mask region id (compute_mask, videoswin.py:272-285)
-//   bit 31       : padding row (index >= N)
-template <int HD>
-__device__ __forceinline__ void win_build_tables(const WinParams& P, int p, int h, int* qrow, int* krow, uint32_t* qinfo,
-                                                 uint32_t* kinfo, float* tab2) {
+// Per-token words: qcode = 4*(code + maxcode), kcode = 4*code (byte offsets; the pair's table slot is qcode - kcode),
+// qreg / kreg = shift-mask region id (compute_mask, videoswin.py:272-285).
+__device__ __forceinline__ bool win_build_tables(const WinParams& P, int p, int h, const Smem& S) {
   const WindowIndex& ix = P.win;
   const int nWw = ix.W / ix.ww, nWh = ix.H / ix.wh, nWd = ix.D / ix.wd;
   int tq = p;
@@ -67,7 +122,8 @@ __device__ __forceinline__ void win_build_tables(const WinParams& P, int p, int 
   const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
   const int hw = ix.wh * ix.ww, dh = ix.wd * ix.wh;
   const int inv_hw = small_inv(hw), inv_ww = small_inv(ix.ww), inv_wh = small_inv(ix.wh), inv_dh = small_inv(dh);
-  const bool shifted = (ix.sd | ix.sh | ix.sw) != 0;
+  // a window carries more than one mask region only where a shifted axis wraps: the last window along that axis
+  const bool masked = (ix.sd > 0 && id == nWd - 1) || (ix.sh > 0 && ih == nWh - 1) || (ix.sw > 0 && iw == nWw - 1);
   for (int i = threadIdx.x; i < P.NP; i += blockDim.x) {
     if (i < ix.N) {
 #pragma unroll
@@ -90,491 +146,521 @@ __device__ __forceinline__ void win_build_tables(const WinParams& P, int p, int 
         int w = cw + ix.sw; if (w >= ix.W) w -= ix.W;
         const int row = ((b * ix.D + d) * ix.H + hh) * ix.W + w;
         uint32_t reg = 0;
-        if (shifted) reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
-                                      ix.region(cw, ix.W, ix.ww, ix.sw));
+        if (masked) reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
+                                     ix.region(cw, ix.W, ix.ww, ix.sw));
         const int code = ld * cH + lh * cW + lw;
-        if (which == 0) { qrow[i] = row; qinfo[i] = (uint32_t)(4 * (code + P.maxcode)) | (reg << 16); }
-        else            { krow[i] = row; kinfo[i] = (uint32_t)(4 * code) | (reg << 16); }
+        if (which == 0) { S.qrow[i] = row; S.qcode[i] = (uint32_t)(4 * (code + P.maxcode)); S.qreg[i] = reg; }
+        else            { S.krow[i] = row; S.kcode[i] = (uint32_t)(4 * code); S.kreg[i] = reg; }
       }
     } else {
-      qrow[i] = -1; krow[i] = -1;
-      qinfo[i] = (uint32_t)(4 * P.maxcode) | 0x80000000u;
-      kinfo[i] = 0x80000000u;
+      S.qrow[i] = -1; S.krow[i] = -1;
+      S.qcode[i] = (uint32_t)(4 * P.maxcode); S.kcode[i] = 0u; S.qreg[i] = 0u; S.kreg[i] = 0u;
     }
   }
-  const int r0 = P.center - P.maxcode;
-  for (int r = threadIdx.x; r < P.n_used; r += blockDim.x) tab2[r] = ix.table[(size_t)(r0 + r) * ix.heads + h] * LOG2E;
+  const float* src = ix.table + (size_t)(P.center - P.maxcode) * ix.heads + h;
+  for (int r = threadIdx.x; r < P.n_used; r += blockDim.x) cp4(sm_addr(S.tab + r), src + (size_t)r * ix.heads);
+  return masked;
 }
 
-// gather NP rows x HD bf16 into a padded shared tile (cp.async, zero-fill for padding rows)
-template <int HD>
+// gather NP rows x 64 B into a swizzled shared tile (cp.async, zero-fill for padding rows)
 __device__ __forceinline__ void win_load_rows(unsigned char* dst, const bf16* src, long long ld, int col0, const int* rows, int NP) {
-  constexpr int PITCH = WinCfg<HD>::PITCH, CH = WinCfg<HD>::CH;
-  for (int c = threadIdx.x; c < NP * CH; c += blockDim.x) {
-    const int r = c / CH, ch = c % CH;
+  const uint32_t d0 = sm_addr(dst);
+  for (int c = threadIdx.x; c < NP * 4; c += blockDim.x) {
+    const int r = c >> 2, ch = c & 3;
     const int gr = rows[r];
-    const bf16* g = src + (size_t)(gr < 0 ? 0 : gr) * ld + col0 + ch * 8;
-    cp_async16(s_u32(dst + r * PITCH + ch * 16), g, gr < 0 ? 0 : 16);
+    cp16(d0 + tile_off(r, ch), src + (size_t)(gr < 0 ? 0 : gr) * ld + col0 + ch * 8, gr < 0 ? 0 : 16);
   }
 }
 
-// score in the log2 domain: s*scale*log2e + bias (+ mask)
-__device__ __forceinline__ float win_score(float s, float sc2, uint32_t qaddr, uint32_t qreg, uint32_t kw, bool shifted) {
-  float v = fmaf(s, sc2, lds_f32(qaddr - (kw & 0xffffu)));
-  if (shifted && ((qreg ^ kw) & 0x00ff0000u)) v += M100_2;
-  return v;
+// ldmatrix addresses.  A-operand / non-transposed B-operand fragments of a 16-row block:
+//   A (rows = M):   lane (m8, r8) -> row base + (m8&1)*8 + r8, chunk ks*2 + (m8>>1)
+//   B (rows = N):   lane (m8, r8) -> row base + (m8>>1)*8 + r8, chunk ks*2 + (m8&1)         (two n-tiles per x4)
+//   B^T (rows = K): lane (m8, r8) -> row base + (m8&1)*8 + r8, chunk dt + (m8>>1), .trans   (two n-tiles per x4)
+// Row bases are multiples of 8, so the swizzle term only depends on r8.
+struct Lane {
+  int lane, g, t4, m8, r8;
+  uint32_t a_off[2];    // A fragment, ks = 0,1 (relative to the 16-row block)
+  uint32_t b_off[2];    // B fragment, ks = 0,1
+  uint32_t bt_off[2];   // B^T fragment, dt = 0,2
+  __device__ __forceinline__ void init() {
+    lane = threadIdx.x & 31; g = lane >> 2; t4 = lane & 3; m8 = lane >> 3; r8 = lane & 7;
+    const int sw = (r8 >> 1) & 3;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      a_off[ks] = (uint32_t)(((m8 & 1) * 8 + r8) * ROWB + (((ks * 2 + (m8 >> 1)) ^ sw) << 4));
+      b_off[ks] = (uint32_t)(((m8 >> 1) * 8 + r8) * ROWB + (((ks * 2 + (m8 & 1)) ^ sw) << 4));
+      bt_off[ks] = (uint32_t)(((m8 & 1) * 8 + r8) * ROWB + (((ks * 2 + (m8 >> 1)) ^ sw) << 4));   // dt = 2*ks
+    }
+  }
+};
+
+static inline size_t win_smem_bytes(int NP, int n_used, bool bwd, int n_dq_warps) {
+  size_t b = (size_t)(bwd ? 4 : 3) * NP * ROWB;   // Q K V (dO)
+  b += (size_t)6 * NP * 4;                        // qrow krow qcode kcode qreg kreg
+  const size_t tab = ((size_t)n_used * 4 + 15) / 16 * 16;
+  b += tab;                                       // bias slice
+  if (bwd) b += (size_t)2 * NP * 4 + (size_t)n_dq_warps * (tab + 16 * 40 * 4);   // lse, -delta, per-warp tables + staging
+  return b + 16;
 }
 
-static inline size_t win_smem_bytes(int HD, int NP, int n_used, bool bwd) {
-  const size_t pitch = HD * 2 + 16;
-  size_t b = (size_t)(bwd ? 4 : 3) * NP * pitch;   // Q K V (dO)
-  b += (size_t)4 * NP * 4;                         // qrow krow qinfo kinfo
-  b += (size_t)n_used * 4;                         // bias slice
-  if (bwd) b += (size_t)n_used * 4 + (size_t)2 * NP * 4 + 16;   // bias-gradient slots, lse, delta, scale words
-  return b + 32;
+__device__ __forceinline__ Smem carve(unsigned char* smem, int NP, bool bwd) {
+  Smem S;
+  S.Qs = smem;
+  S.Ks = S.Qs + NP * ROWB;
+  S.Vs = S.Ks + NP * ROWB;
+  S.dOs = S.Vs + NP * ROWB;
+  S.qrow = (int*)(bwd ? S.dOs + NP * ROWB : S.dOs);
+  S.krow = S.qrow + NP;
+  S.qcode = (uint32_t*)(S.krow + NP);
+  S.kcode = S.qcode + NP;
+  S.qreg = S.kcode + NP;
+  S.kreg = S.qreg + NP;
+  S.tab = (float*)(S.kreg + NP);
+  return S;
 }
 
 // ==========================================================================================
 // forward
 // ==========================================================================================
-template <int HD>
+// One 64-key block of one 16-query block.  TAIL: the block holds padding keys and fewer than four 16-key pairs.
+template <bool MASKED, bool TAIL>
+__device__ __forceinline__ void fwd_block(const Lane& L, uint32_t Kb, uint32_t Vb, uint32_t kcode_b, uint32_t kreg_b,
+                                          int keys_left, const uint32_t (&qf)[2][4], const uint32_t (&qaddr)[2],
+                                          const uint32_t (&qrg)[2], float scale, float (&o)[5][4], float (&mrow)[2]) {
+  const int npair = TAIL ? min(4, (keys_left + 15) >> 4) : 4;
+  float s[8][4];
+#pragma unroll
+  for (int pr = 0; pr < 4; ++pr)
+    if (!TAIL || pr < npair) {
+      uint32_t b[4];
+      ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[0]);
+      mma_init(s[pr * 2], qf[0], b, 0.f, 0.f, 0.f, 0.f);
+      mma_init(s[pr * 2 + 1], qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+      ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[1]);
+      mma_acc(s[pr * 2], qf[1], b);
+      mma_acc(s[pr * 2 + 1], qf[1], b + 2);
+    }
+  float mnew[2] = {mrow[0], mrow[1]};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+    if (!TAIL || (nt >> 1) < npair) {
+      const uint2 kc = ld_v2u32(kcode_b + 4u * (uint32_t)(nt * 8 + L.t4 * 2));
+      uint2 kr = make_uint2(0u, 0u);
+      if (MASKED) kr = ld_v2u32(kreg_b + 4u * (uint32_t)(nt * 8 + L.t4 * 2));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        float v = fmaf(s[nt][e], scale, ld_f32(qaddr[r] - ((e & 1) ? kc.y : kc.x)));
+        if (MASKED && qrg[r] != ((e & 1) ? kr.y : kr.x)) v += kMask;
+        if (TAIL && nt * 8 + L.t4 * 2 + (e & 1) >= keys_left) v = -INFINITY;
+        s[nt][e] = v;
+        mnew[r] = fmaxf(mnew[r], v);
+      }
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
+    mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
+  }
+  float ml[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {   // block 0 always holds real keys, so mnew is finite from the first block on
+    const float corr = ex2((mrow[r] - mnew[r]) * kLog2e);
+    mrow[r] = mnew[r];
+    ml[r] = -mnew[r] * kLog2e;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { o[i][r * 2] *= corr; o[i][r * 2 + 1] *= corr; }
+  }
+  const uint32_t ones[2] = {0x3f803f80u, 0x3f803f80u};   // bf16 1.0 pairs: column block of ones -> row sums of P
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    if (!TAIL || kk < npair) {
+      uint32_t pf[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int nt = kk * 2 + hf;
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pv[e] = ex2(fmaf(s[nt][e], kLog2e, ml[e >> 1]));
+        pf[hf * 2 + 0] = pack2(pv[0], pv[1]);
+        pf[hf * 2 + 1] = pack2(pv[2], pv[3]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t b[4];
+        ldsm4t(b, Vb + kk * 16 * ROWB + L.bt_off[ks]);
+        mma_acc(o[ks * 2], pf, b);
+        mma_acc(o[ks * 2 + 1], pf, b + 2);
+      }
+      mma_acc(o[4], pf, ones);
+    }
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void fwd_rows(const WinParams& P, const Smem& S, const Lane& L, int p, int h, int rb) {
+  const int N = P.win.N;
+  const uint32_t Qs = sm_addr(S.Qs), Ks = sm_addr(S.Ks), Vs = sm_addr(S.Vs);
+  const uint32_t tab_s = sm_addr(S.tab), kcode_s = sm_addr(S.kcode), kreg_s = sm_addr(S.kreg);
+  uint32_t qf[2][4];
+  ldsm4(qf[0], Qs + rb * 16 * ROWB + L.a_off[0]);
+  ldsm4(qf[1], Qs + rb * 16 * ROWB + L.a_off[1]);
+  const int i0 = rb * 16 + L.g;
+  const uint32_t qaddr[2] = {tab_s + S.qcode[i0], tab_s + S.qcode[i0 + 8]};
+  const uint32_t qrg[2] = {S.qreg[i0], S.qreg[i0 + 8]};
+  float o[5][4];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY};
+  const int nfull = N >> 6;
+#pragma unroll 1
+  for (int kb = 0; kb < nfull; ++kb)
+    fwd_block<MASKED, false>(L, Ks + kb * 64 * ROWB, Vs + kb * 64 * ROWB, kcode_s + kb * 256, kreg_s + kb * 256, 64, qf,
+                             qaddr, qrg, P.scale, o, mrow);
+  if (N & 63)
+    fwd_block<MASKED, true>(L, Ks + nfull * 64 * ROWB, Vs + nfull * 64 * ROWB, kcode_s + nfull * 256, kreg_s + nfull * 256,
+                            N - nfull * 64, qf, qaddr, qrg, P.scale, o, mrow);
+  const int col0 = h * HD;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + r * 8;
+    if (i < N) {
+      const float l = o[4][r * 2];   // every column of the ones block carries the row sum
+      const float inv = 1.f / l;
+      bf16* dst = P.O + (size_t)S.qrow[i] * P.ldo + col0;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt)
+        *(uint32_t*)(dst + dt * 8 + L.t4 * 2) = pack2(o[dt][r * 2] * inv, o[dt][r * 2 + 1] * inv);
+      if (L.t4 == 0) P.lse[((size_t)p * P.heads + h) * N + i] = mrow[r] + log2f(l) * kLn2;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 2)
 window_fwd_kernel(WinParams P) {
-  constexpr int PITCH = WinCfg<HD>::PITCH;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int NP = P.NP;
-  unsigned char* Qs = smem;
-  unsigned char* Ks = Qs + NP * PITCH;
-  unsigned char* Vs = Ks + NP * PITCH;
-  int* qrow = (int*)(Vs + NP * PITCH);
-  int* krow = qrow + NP;
-  uint32_t* qinfo = (uint32_t*)(krow + NP);
-  uint32_t* kinfo = qinfo + NP;
-  float* tab2 = (float*)(kinfo + NP);
+  const Smem S = carve(smem, P.NP, false);
   const int p = blockIdx.x, h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  const int nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int C = P.heads * HD, col0 = h * HD;
-  win_build_tables<HD>(P, p, h, qrow, krow, qinfo, kinfo, tab2);
+  const bool masked = win_build_tables(P, p, h, S);
   __syncthreads();
-  win_load_rows<HD>(Qs, P.qkv, P.ld, col0, qrow, NP);
-  win_load_rows<HD>(Ks, P.qkv + C, P.ld, col0, krow, NP);
-  win_load_rows<HD>(Vs, P.qkv + 2 * C, P.ld, col0, krow, NP);
-  cp_async_commit();
-  cp_async_wait<0>();
+  win_load_rows(S.Qs, P.qkv, P.ld, col0, S.qrow, P.NP);
+  win_load_rows(S.Ks, P.qkv + C, P.ld, col0, S.krow, P.NP);
+  win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.krow, P.NP);
+  cp_commit();
+  cp_wait_all();
   __syncthreads();
-
-  const int N = P.win.N;
-  const bool shifted = (P.win.sd | P.win.sh | P.win.sw) != 0;
-  const float sc2 = P.scale * LOG2E;
-  const uint32_t tab2_s = s_u32(tab2), kinfo_s = s_u32(kinfo);
-  const int m8 = lane >> 3, r8 = lane & 7;
-  const int nrb = NP >> 4;
-  const int nkb = (N + 63) >> 6;
-  for (int rb = warp; rb < nrb; rb += nwarps) {
-    uint32_t qf[HD / 16][4];
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks)
-      ldsm_x4(qf[ks], s_u32(Qs + (rb * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
-    const int i0 = rb * 16 + g;
-    const uint32_t qw0 = qinfo[i0], qw1 = qinfo[i0 + 8];
-    const uint32_t qaddr[2] = {tab2_s + (qw0 & 0xffffu), tab2_s + (qw1 & 0xffffu)};
-    const uint32_t qreg[2] = {qw0, qw1};
-    float o[HD / 8][4];
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int k0 = kb * 64;
-      const int npair = min(4, (N - k0 + 15) >> 4);   // 16-key pairs of n-tiles with at least one real key
-      const unsigned char* Kb = Ks + k0 * PITCH;
-      const unsigned char* Vb = Vs + k0 * PITCH;
-      float s[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks)
-#pragma unroll
-        for (int pr = 0; pr < 4; ++pr)
-          if (pr < npair) {
-            uint32_t b[4];
-            ldsm_x4(b, s_u32(Kb + ((pr * 2 + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-            mma16816(s[pr * 2], qf[ks], b);
-            mma16816(s[pr * 2 + 1], qf[ks], b + 2);
-          }
-      float mnew[2] = {mrow[0], mrow[1]};
-      const bool ragged = k0 + npair * 16 > N;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-        if ((nt >> 1) < npair) {
-          const uint2 kj = lds_v2u32(kinfo_s + 4u * (uint32_t)(k0 + nt * 8 + t4 * 2));
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t kw = (e & 1) ? kj.y : kj.x;
-            float v = win_score(s[nt][e], sc2, qaddr[e >> 1], qreg[e >> 1], kw, shifted);
-            if (ragged && (kw >> 31)) v = -INFINITY;
-            s[nt][e] = v;
-            mnew[e >> 1] = fmaxf(mnew[e >> 1], v);
-          }
-        }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
-        mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
-      }
-      float corr[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {   // every row sees at least one real key in block 0, so mnew is finite
-        corr[r] = fast_exp2(mrow[r] - mnew[r]);
-        mrow[r] = mnew[r];
-        lrow[r] *= corr[r];
-      }
-#pragma unroll
-      for (int i = 0; i < HD / 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
-      uint32_t pf[4][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-        if ((nt >> 1) < npair) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float pv = fast_exp2(s[nt][e] - mnew[e >> 1]);
-            s[nt][e] = pv;
-            lrow[e >> 1] += pv;
-          }
-          pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(s[nt][0], s[nt][1]);
-          pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(s[nt][2], s[nt][3]);
-        }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        if (kk < npair) {
-#pragma unroll
-          for (int dt = 0; dt < HD / 8; dt += 2) {
-            uint32_t b[4];
-            ldsm_x4_t(b, s_u32(Vb + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-            mma16816(o[dt], pf[kk], b);
-            mma16816(o[dt + 1], pf[kk], b + 2);
-          }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
-      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int i = i0 + r * 8;
-      if (i < N) {
-        const float inv = 1.f / lrow[r];
-        bf16* dst = P.O + (size_t)qrow[i] * P.ldo + col0;
-#pragma unroll
-        for (int dt = 0; dt < HD / 8; ++dt)
-          *(uint32_t*)(dst + dt * 8 + t4 * 2) = pack_bf16(o[dt][r * 2] * inv, o[dt][r * 2 + 1] * inv);
-        if (t4 == 0) P.lse[((size_t)p * P.heads + h) * N + i] = (mrow[r] + log2f(lrow[r])) * LN2;
-      }
-    }
+  Lane L;
+  L.init();
+  const int nrb = P.NP >> 4;
+  if (masked) {
+    for (int rb = warp; rb < nrb; rb += nwarps) fwd_rows<true>(P, S, L, p, h, rb);
+  } else {
+    for (int rb = warp; rb < nrb; rb += nwarps) fwd_rows<false>(P, S, L, p, h, rb);
   }
 }
 
 // ==========================================================================================
 // backward
 // ==========================================================================================
-template <int HD>
-__global__ void __launch_bounds__(256, 2)
-window_bwd_kernel(WinParams P) {
-  constexpr int PITCH = WinCfg<HD>::PITCH, CH = WinCfg<HD>::CH;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int NP = P.NP;
-  unsigned char* Qs = smem;
-  unsigned char* Ks = Qs + NP * PITCH;
-  unsigned char* Vs = Ks + NP * PITCH;
-  unsigned char* dOs = Vs + NP * PITCH;
-  int* qrow = (int*)(dOs + NP * PITCH);
-  int* krow = qrow + NP;
-  uint32_t* qinfo = (uint32_t*)(krow + NP);
-  uint32_t* kinfo = qinfo + NP;
-  float* tab2 = (float*)(kinfo + NP);
-  int* dtab = (int*)(tab2 + P.n_used);
-  float* lse_s = (float*)(dtab + P.n_used);   // log2 domain; +inf for padding rows
-  float* del_s = lse_s + NP;
-  int* mx = (int*)(del_s + NP);               // [0] max|dO row|^2, [1] max|V row|^2 (non-negative floats as ints)
-  const int p = blockIdx.x, h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  const int nwarps = blockDim.x >> 5;
-  const int C = P.heads * HD, col0 = h * HD;
+// dQ for one 16-query block; the block's dS also goes into this warp's private bias-gradient table.
+template <bool MASKED>
+__device__ __forceinline__ void bwd_dq_unit(const WinParams& P, const Smem& S, const Lane& L, int h, int rb, uint32_t lse_s,
+                                            uint32_t ndel_s, uint32_t gtab_s, uint32_t stg_s) {
   const int N = P.win.N;
-  win_build_tables<HD>(P, p, h, qrow, krow, qinfo, kinfo, tab2);
-  for (int i = threadIdx.x; i < P.n_used; i += blockDim.x) dtab[i] = 0;
-  if (threadIdx.x < 2) mx[threadIdx.x] = 0;
-  __syncthreads();
-  win_load_rows<HD>(Qs, P.qkv, P.ld, col0, qrow, NP);
-  win_load_rows<HD>(Ks, P.qkv + C, P.ld, col0, krow, NP);
-  win_load_rows<HD>(Vs, P.qkv + 2 * C, P.ld, col0, krow, NP);
-  win_load_rows<HD>(dOs, P.dO, P.ldo, col0, qrow, NP);
-  cp_async_commit();
-  for (int i = threadIdx.x; i < NP; i += blockDim.x)
-    lse_s[i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] * LOG2E : INFINITY;
-  cp_async_wait<0>();
-  __syncthreads();
-  {
-    // delta_i = dO_i . O_i (O rows straight from global), plus the row-norm maxima that size the fixed-point scale
-    float mdo = 0.f, mv = 0.f;
-    for (int c = threadIdx.x; c < NP * CH; c += blockDim.x) {   // NP*CH is a multiple of 32: whole warps iterate
-      const int r = c / CH, ch = c % CH;
-      const int gr = qrow[r];
-      float d = 0.f, n2 = 0.f, v2 = 0.f;
-      const uint4 a = *(const uint4*)(dOs + r * PITCH + ch * 16);
-      const uint4 vv = *(const uint4*)(Vs + r * PITCH + ch * 16);
-      uint4 o4 = make_uint4(0, 0, 0, 0);
-      if (gr >= 0) o4 = *(const uint4*)(P.O + (size_t)gr * P.ldo + col0 + ch * 8);
-      const __nv_bfloat162* pa = (const __nv_bfloat162*)&a;
-      const __nv_bfloat162* po = (const __nv_bfloat162*)&o4;
-      const __nv_bfloat162* pv = (const __nv_bfloat162*)&vv;
+  const uint32_t Qs = sm_addr(S.Qs), Ks = sm_addr(S.Ks), Vs = sm_addr(S.Vs), dOs = sm_addr(S.dOs);
+  const uint32_t tab_s = sm_addr(S.tab), kcode_s = sm_addr(S.kcode), kreg_s = sm_addr(S.kreg);
+  uint32_t qf[2][4], dof[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 fa = __bfloat1622float2(pa[j]), fo = __bfloat1622float2(po[j]), fv = __bfloat1622float2(pv[j]);
-        d += fa.x * fo.x + fa.y * fo.y;
-        n2 += fa.x * fa.x + fa.y * fa.y;
-        v2 += fv.x * fv.x + fv.y * fv.y;
-      }
-#pragma unroll
-      for (int sft = 1; sft < CH; sft <<= 1) {
-        d += __shfl_xor_sync(0xffffffffu, d, sft);
-        n2 += __shfl_xor_sync(0xffffffffu, n2, sft);
-        v2 += __shfl_xor_sync(0xffffffffu, v2, sft);
-      }
-      if (ch == 0) del_s[r] = d;
-      mdo = fmaxf(mdo, n2);
-      mv = fmaxf(mv, v2);
-    }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) {
-      mdo = fmaxf(mdo, __shfl_xor_sync(0xffffffffu, mdo, sft));
-      mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, sft));
-    }
-    if (lane == 0) {
-      atomicMax(&mx[0], __float_as_int(mdo));
-      atomicMax(&mx[1], __float_as_int(mv));
-    }
+  for (int ks = 0; ks < 2; ++ks) {
+    ldsm4(qf[ks], Qs + rb * 16 * ROWB + L.a_off[ks]);
+    ldsm4(dof[ks], dOs + rb * 16 * ROWB + L.a_off[ks]);
   }
-  __syncthreads();
-  // |dS_ij| = |p (dp - delta)| <= 2 |dO_i| max|V|; at most N contributions share one bias slot in this CTA.
-  // fixed-point scale: the largest power of two with  N * 2 |dO|max |V|max * scale < 2^30
-  float fx_scale, fx_inv;
-  {
-    const float bound = 2.f * (float)N * sqrtf(__int_as_float(mx[0]) * __int_as_float(mx[1]));
-    int e = 0;
-    if (bound > 0.f) { (void)frexpf(bound, &e); }   // bound = m * 2^e, m in [0.5, 1)
-    e = max(-60, min(60, 30 - e));
-    fx_scale = exp2f((float)e);
-    fx_inv = exp2f((float)-e);
-  }
-  const bool shifted = (P.win.sd | P.win.sh | P.win.sw) != 0;
-  const float sc = P.scale, sc2 = P.scale * LOG2E;
-  const uint32_t tab2_s = s_u32(tab2), kinfo_s = s_u32(kinfo), qinfo_s = s_u32(qinfo), dtab_s = s_u32(dtab);
-  const uint32_t lse_ss = s_u32(lse_s), del_ss = s_u32(del_s);
-  const int m8 = lane >> 3, r8 = lane & 7;
-  const int nrb = NP >> 4;
-  const int nhalf = (N + 31) >> 5;   // 32-wide sweeps over the other dimension (rows >= N are zero / masked)
+  const int i0 = rb * 16 + L.g;
+  const uint32_t qaddr[2] = {tab_s + S.qcode[i0], tab_s + S.qcode[i0 + 8]};
+  const uint32_t qrg[2] = {S.qreg[i0], S.qreg[i0 + 8]};
+  const float nlse[2] = {-ld_f32(lse_s + 4u * i0) * kLog2e, -ld_f32(lse_s + 4u * (i0 + 8)) * kLog2e};   // -inf on padding rows
+  const float ndel[2] = {ld_f32(ndel_s + 4u * i0), ld_f32(ndel_s + 4u * (i0 + 8))};
+  // row r of the block is folded into the gradient table at byte offset qcode(row r) - kcode(key)
+  const uint32_t my_qcode = S.qcode[rb * 16 + (L.lane & 15)];
   const bool want_dtab = P.dtable != nullptr;
-
-  for (int unit = warp; unit < 2 * nrb; unit += nwarps) {
-    if (unit < nrb) {
-      // ------------------------------ dQ for 16 queries ------------------------------
-      const int rb = unit;
-      uint32_t qf[HD / 16][4], dof[HD / 16][4];
+  float dq[4][4];
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
-        ldsm_x4(qf[ks], s_u32(Qs + (rb * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
-        ldsm_x4(dof[ks], s_u32(dOs + (rb * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
-      }
-      const int i0 = rb * 16 + g;
-      const uint32_t qw0 = qinfo[i0], qw1 = qinfo[i0 + 8];
-      const uint32_t qoff[2] = {qw0 & 0xffffu, qw1 & 0xffffu};
-      const uint32_t qreg[2] = {qw0, qw1};
-      const float lse2[2] = {lse_s[i0], lse_s[i0 + 8]};   // +inf on padding rows -> p = 0
-      const float del[2] = {del_s[i0], del_s[i0 + 8]};
-      float dq[HD / 8][4];
-#pragma unroll
-      for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  for (int i = 0; i < 4; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const int nsweep = (N + 31) >> 5;
 #pragma unroll 1
-      for (int hb = 0; hb < nhalf; ++hb) {
-        const int k0 = hb * 32;
-        const unsigned char* Kb = Ks + k0 * PITCH;
-        const unsigned char* Vb = Vs + k0 * PITCH;
-        const int npair = min(2, (N - k0 + 15) >> 4);
-        float s[4][4], dp[4][4];
+  for (int hb = 0; hb < nsweep; ++hb) {
+    const int k0 = hb * 32;
+    const int left = N - k0;                        // real keys from k0 on
+    const int npair = min(2, (left + 15) >> 4);
+    const uint32_t Kb = Ks + k0 * ROWB, Vb = Vs + k0 * ROWB;
+    float s[4][4], dp[4][4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-#pragma unroll
-          for (int pr = 0; pr < 2; ++pr)
-            if (pr < npair) {
-              uint32_t b[4];
-              ldsm_x4(b, s_u32(Kb + ((pr * 2 + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-              mma16816(s[pr * 2], qf[ks], b);
-              mma16816(s[pr * 2 + 1], qf[ks], b + 2);
-              ldsm_x4(b, s_u32(Vb + ((pr * 2 + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-              mma16816(dp[pr * 2], dof[ks], b);
-              mma16816(dp[pr * 2 + 1], dof[ks], b + 2);
-            }
-        uint32_t dsf[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          float ds[4] = {0.f, 0.f, 0.f, 0.f};
-          if ((nt >> 1) < npair) {
-            const uint2 kj = lds_v2u32(kinfo_s + 4u * (uint32_t)(k0 + nt * 8 + t4 * 2));
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int r = e >> 1;
-              const uint32_t kw = (e & 1) ? kj.y : kj.x;
-              const float v = win_score(s[nt][e], sc2, tab2_s + qoff[r], qreg[r], kw, shifted);
-              float pr_ = fast_exp2(v - lse2[r]);
-              if (kw >> 31) pr_ = 0.f;
-              const float d = pr_ * (dp[nt][e] - del[r]);
-              if (want_dtab) {
-                const int q = __float2int_rn(d * fx_scale);
-                asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(dtab_s + qoff[r] - (kw & 0xffffu)), "r"(q) : "memory");
-              }
-              ds[e] = d * sc;
-            }
-          }
-          dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
-          dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-          if (kk < npair) {
-#pragma unroll
-            for (int dt = 0; dt < HD / 8; dt += 2) {
-              uint32_t b[4];
-              ldsm_x4_t(b, s_u32(Kb + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-              mma16816(dq[dt], dsf[kk], b);
-              mma16816(dq[dt + 1], dsf[kk], b + 2);
-            }
-          }
+    for (int pr = 0; pr < 2; ++pr)
+      if (pr < npair) {
+        uint32_t b[4];
+        ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[0]);
+        mma_init(s[pr * 2], qf[0], b, 0.f, 0.f, 0.f, 0.f);
+        mma_init(s[pr * 2 + 1], qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+        ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[1]);
+        mma_acc(s[pr * 2], qf[1], b);
+        mma_acc(s[pr * 2 + 1], qf[1], b + 2);
+        ldsm4(b, Vb + pr * 16 * ROWB + L.b_off[0]);   // dP - delta: the accumulator starts at -delta_i
+        mma_init(dp[pr * 2], dof[0], b, ndel[0], ndel[0], ndel[1], ndel[1]);
+        mma_init(dp[pr * 2 + 1], dof[0], b + 2, ndel[0], ndel[0], ndel[1], ndel[1]);
+        ldsm4(b, Vb + pr * 16 * ROWB + L.b_off[1]);
+        mma_acc(dp[pr * 2], dof[1], b);
+        mma_acc(dp[pr * 2 + 1], dof[1], b + 2);
       }
+    uint32_t dsf[2][4];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i = i0 + r * 8;
-        if (i < N) {
-          bf16* dst = P.dqkv + (size_t)qrow[i] * P.lddqkv + col0;
+    for (int nt = 0; nt < 4; ++nt) {
+      float ds[4] = {0.f, 0.f, 0.f, 0.f};
+      if ((nt >> 1) < npair) {
+        const uint2 kc = ld_v2u32(kcode_s + 4u * (uint32_t)(k0 + nt * 8 + L.t4 * 2));
+        uint2 kr = make_uint2(0u, 0u);
+        if (MASKED) kr = ld_v2u32(kreg_s + 4u * (uint32_t)(k0 + nt * 8 + L.t4 * 2));
 #pragma unroll
-          for (int dt = 0; dt < HD / 8; ++dt)
-            *(uint32_t*)(dst + dt * 8 + t4 * 2) = pack_bf16(dq[dt][r * 2], dq[dt][r * 2 + 1]);
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          float v = fmaf(s[nt][e], P.scale, ld_f32(qaddr[r] - ((e & 1) ? kc.y : kc.x)));
+          if (MASKED && qrg[r] != ((e & 1) ? kr.y : kr.x)) v += kMask;
+          float pr_ = ex2(fmaf(v, kLog2e, nlse[r]));
+          if (nt * 8 + L.t4 * 2 + (e & 1) >= left) pr_ = 0.f;   // padding key (only ever true in the last sweep)
+          ds[e] = pr_ * dp[nt][e];
         }
       }
-    } else {
-      // ------------------------------ dK, dV for 16 keys ------------------------------
-      const int jb = unit - nrb;
-      uint32_t kf[HD / 16][4], vf[HD / 16][4];
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
-        ldsm_x4(kf[ks], s_u32(Ks + (jb * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
-        ldsm_x4(vf[ks], s_u32(Vs + (jb * 16 + (m8 & 1) * 8 + r8) * PITCH + (ks * 16 + (m8 >> 1) * 8) * 2));
+      if (want_dtab) {   // stage the fp32 tile [16 rows][32 keys], row pitch 40 floats
+        stv_v2f32(stg_s + 4u * (uint32_t)(L.g * 40 + nt * 8 + L.t4 * 2), ds[0], ds[1]);
+        stv_v2f32(stg_s + 4u * (uint32_t)((L.g + 8) * 40 + nt * 8 + L.t4 * 2), ds[2], ds[3]);
       }
-      const int j0 = jb * 16 + g;
-      const uint32_t kinf[2] = {kinfo[j0], kinfo[j0 + 8]};   // padding keys: K/V rows are zero, results dropped
-      float dk[HD / 8][4], dv[HD / 8][4];
+      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack2(ds[0], ds[1]);
+      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
+    }
 #pragma unroll
-      for (int i = 0; i < HD / 8; ++i)
+    for (int kk = 0; kk < 2; ++kk)
+      if (kk < npair) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
-#pragma unroll 1
-      for (int hb = 0; hb < nhalf; ++hb) {
-        const int q0 = hb * 32;
-        const unsigned char* Qb = Qs + q0 * PITCH;
-        const unsigned char* dOb = dOs + q0 * PITCH;
-        const int npair = min(2, (N - q0 + 15) >> 4);
-        float s[4][4], dp[4][4];   // rows = keys (g, g+8), cols = queries
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-#pragma unroll
-          for (int pr = 0; pr < 2; ++pr)
-            if (pr < npair) {
-              uint32_t b[4];
-              ldsm_x4(b, s_u32(Qb + ((pr * 2 + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-              mma16816(s[pr * 2], kf[ks], b);
-              mma16816(s[pr * 2 + 1], kf[ks], b + 2);
-              ldsm_x4(b, s_u32(dOb + ((pr * 2 + (m8 >> 1)) * 8 + r8) * PITCH + (ks * 16 + (m8 & 1) * 8) * 2));
-              mma16816(dp[pr * 2], vf[ks], b);
-              mma16816(dp[pr * 2 + 1], vf[ks], b + 2);
-            }
-        uint32_t pf[2][4], dsf[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
-          if ((nt >> 1) < npair) {
-            const uint32_t ib = (uint32_t)(q0 + nt * 8 + t4 * 2);   // two consecutive queries (columns of S^T)
-            const uint2 qi2 = lds_v2u32(qinfo_s + 4u * ib);
-            const float2 l2 = lds_v2f32(lse_ss + 4u * ib);
-            const float2 d2 = lds_v2f32(del_ss + 4u * ib);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int r = e >> 1;
-              const uint32_t qw = (e & 1) ? qi2.y : qi2.x;
-              const float v = win_score(s[nt][e], sc2, tab2_s + (qw & 0xffffu), qw, kinf[r], shifted);
-              const float pr_ = fast_exp2(v - ((e & 1) ? l2.y : l2.x));   // padding queries carry lse = +inf -> 0
-              pv[e] = pr_;
-              ds[e] = pr_ * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * sc;
-            }
-          }
-          pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
-          pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
-          dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
-          dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t b[4];
+          ldsm4t(b, Kb + kk * 16 * ROWB + L.bt_off[ks]);
+          mma_acc(dq[ks * 2], dsf[kk], b);
+          mma_acc(dq[ks * 2 + 1], dsf[kk], b + 2);
         }
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk)   // contraction over the 16-query pairs of this sweep
-          if (kk < npair) {
-#pragma unroll
-            for (int dt = 0; dt < HD / 8; dt += 2) {
-              uint32_t b[4];
-              ldsm_x4_t(b, s_u32(dOb + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-              mma16816(dv[dt], pf[kk], b);
-              mma16816(dv[dt + 1], pf[kk], b + 2);
-              ldsm_x4_t(b, s_u32(Qb + (kk * 16 + (m8 & 1) * 8 + r8) * PITCH + ((dt + (m8 >> 1)) * 8) * 2));
-              mma16816(dk[dt], dsf[kk], b);
-              mma16816(dk[dt + 1], dsf[kk], b + 2);
-            }
-          }
       }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int j = j0 + r * 8;
-        if (j < N) {
-          bf16* dstk = P.dqkv + (size_t)krow[j] * P.lddqkv + C + col0;
-          bf16* dstv = dstk + C;
-#pragma unroll
-          for (int dt = 0; dt < HD / 8; ++dt) {
-            *(uint32_t*)(dstk + dt * 8 + t4 * 2) = pack_bf16(dk[dt][r * 2], dk[dt][r * 2 + 1]);
-            *(uint32_t*)(dstv + dt * 8 + t4 * 2) = pack_bf16(dv[dt][r * 2], dv[dt][r * 2 + 1]);
-          }
-        }
+    if (want_dtab) {
+      // fold the staged tile into the private table, one query row per step: lane l owns key k0 + l, and
+      // within a row distinct keys hit distinct slots
+      __syncwarp();
+      const bool live = L.lane < left;
+      const uint32_t kc_l = S.kcode[min(k0 + L.lane, P.NP - 1)];
+#pragma unroll 4
+      for (int r = 0; r < 16; ++r) {
+        const uint32_t slot = gtab_s + __shfl_sync(0xffffffffu, my_qcode, r) - kc_l;
+        const float add = ldv_f32(stg_s + 4u * (uint32_t)(r * 40 + L.lane));
+        if (live) stv_f32(slot, ldv_f32(slot) + add);
+        __syncwarp();
       }
     }
   }
-  if (want_dtab) {
-    __syncthreads();
-    const int r0 = P.center - P.maxcode;
-    for (int r = threadIdx.x; r < P.n_used; r += blockDim.x) {
-      const int q = dtab[r];
-      if (q != 0) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], (float)q * fx_inv);
+  const int col0 = h * HD;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + r * 8;
+    if (i < N) {
+      bf16* dst = P.dqkv + (size_t)S.qrow[i] * P.lddqkv + col0;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt)
+        *(uint32_t*)(dst + dt * 8 + L.t4 * 2) = pack2(dq[dt][r * 2] * P.scale, dq[dt][r * 2 + 1] * P.scale);
     }
   }
 }
 
+// dK, dV for one 16-key block.
+template <bool MASKED>
+__device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, const Lane& L, int h, int jb, uint32_t lse_s,
+                                             uint32_t ndel_s) {
+  const int N = P.win.N;
+  const uint32_t Qs = sm_addr(S.Qs), Ks = sm_addr(S.Ks), Vs = sm_addr(S.Vs), dOs = sm_addr(S.dOs);
+  const uint32_t tab_s = sm_addr(S.tab), qcode_s = sm_addr(S.qcode), qreg_s = sm_addr(S.qreg);
+  uint32_t kf[2][4], vf[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    ldsm4(kf[ks], Ks + jb * 16 * ROWB + L.a_off[ks]);
+    ldsm4(vf[ks], Vs + jb * 16 * ROWB + L.a_off[ks]);
+  }
+  const int j0 = jb * 16 + L.g;   // keys j0, j0+8 (padding keys: K/V rows are zero, results dropped)
+  const uint32_t kaddr[2] = {tab_s - S.kcode[j0], tab_s - S.kcode[j0 + 8]};
+  const uint32_t krg[2] = {S.kreg[j0], S.kreg[j0 + 8]};
+  float dk[4][4], dv[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
+  const int nsweep = (N + 31) >> 5;
+#pragma unroll 1
+  for (int hb = 0; hb < nsweep; ++hb) {
+    const int q0 = hb * 32;
+    const int npair = min(2, (N - q0 + 15) >> 4);
+    const uint32_t Qb = Qs + q0 * ROWB, dOb = dOs + q0 * ROWB;
+    float s[4][4], dp[4][4];   // rows = keys (g, g+8), cols = queries
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr)
+      if (pr < npair) {
+        uint32_t b[4];
+        const float2 nd0 = ld_v2f32(ndel_s + 4u * (uint32_t)(q0 + pr * 16 + L.t4 * 2));       // -delta of the two query columns
+        const float2 nd1 = ld_v2f32(ndel_s + 4u * (uint32_t)(q0 + pr * 16 + 8 + L.t4 * 2));
+        ldsm4(b, Qb + pr * 16 * ROWB + L.b_off[0]);
+        mma_init(s[pr * 2], kf[0], b, 0.f, 0.f, 0.f, 0.f);
+        mma_init(s[pr * 2 + 1], kf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+        ldsm4(b, Qb + pr * 16 * ROWB + L.b_off[1]);
+        mma_acc(s[pr * 2], kf[1], b);
+        mma_acc(s[pr * 2 + 1], kf[1], b + 2);
+        ldsm4(b, dOb + pr * 16 * ROWB + L.b_off[0]);
+        mma_init(dp[pr * 2], vf[0], b, nd0.x, nd0.y, nd0.x, nd0.y);
+        mma_init(dp[pr * 2 + 1], vf[0], b + 2, nd1.x, nd1.y, nd1.x, nd1.y);
+        ldsm4(b, dOb + pr * 16 * ROWB + L.b_off[1]);
+        mma_acc(dp[pr * 2], vf[1], b);
+        mma_acc(dp[pr * 2 + 1], vf[1], b + 2);
+      }
+    uint32_t pf[2][4], dsf[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+      if ((nt >> 1) < npair) {
+        const uint32_t ib = (uint32_t)(q0 + nt * 8 + L.t4 * 2);   // two consecutive queries (columns of S^T)
+        const uint2 qc = ld_v2u32(qcode_s + 4u * ib);
+        const float2 l2 = ld_v2f32(lse_s + 4u * ib);              // +inf on padding queries -> p = 0
+        uint2 qr = make_uint2(0u, 0u);
+        if (MASKED) qr = ld_v2u32(qreg_s + 4u * ib);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          float v = fmaf(s[nt][e], P.scale, ld_f32(kaddr[r] + ((e & 1) ? qc.y : qc.x)));
+          if (MASKED && krg[r] != ((e & 1) ? qr.y : qr.x)) v += kMask;
+          const float pr_ = ex2((v - ((e & 1) ? l2.y : l2.x)) * kLog2e);
+          pv[e] = pr_;
+          ds[e] = pr_ * dp[nt][e];
+        }
+      }
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack2(pv[0], pv[1]);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack2(pv[2], pv[3]);
+      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack2(ds[0], ds[1]);
+      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)   // contraction over the 16-query pairs of this sweep
+      if (kk < npair) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t b[4];
+          ldsm4t(b, dOb + kk * 16 * ROWB + L.bt_off[ks]);
+          mma_acc(dv[ks * 2], pf[kk], b);
+          mma_acc(dv[ks * 2 + 1], pf[kk], b + 2);
+          ldsm4t(b, Qb + kk * 16 * ROWB + L.bt_off[ks]);
+          mma_acc(dk[ks * 2], dsf[kk], b);
+          mma_acc(dk[ks * 2 + 1], dsf[kk], b + 2);
+        }
+      }
+  }
+  const int C = P.heads * HD, col0 = h * HD;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = j0 + r * 8;
+    if (j < N) {
+      bf16* dstk = P.dqkv + (size_t)S.krow[j] * P.lddqkv + C + col0;
+      bf16* dstv = dstk + C;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) {
+        *(uint32_t*)(dstk + dt * 8 + L.t4 * 2) = pack2(dk[dt][r * 2] * P.scale, dk[dt][r * 2 + 1] * P.scale);
+        *(uint32_t*)(dstv + dt * 8 + L.t4 * 2) = pack2(dv[dt][r * 2], dv[dt][r * 2 + 1]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(448, 1)
+window_bwd_kernel(WinParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int NP = P.NP;
+  const Smem S = carve(smem, NP, true);
+  float* lse_sm = (float*)((unsigned char*)S.tab + P.tab_stride);   // natural-log lse; +inf on padding rows
+  float* ndel_sm = lse_sm + NP;                                      // -delta_i
+  unsigned char* priv = (unsigned char*)(ndel_sm + NP);              // per dq warp: [tab_stride] table + [16][40] staging
+  const int priv_stride = P.tab_stride + 16 * 40 * 4;
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int C = P.heads * HD, col0 = h * HD;
+  const int N = P.win.N;
+  const bool masked = win_build_tables(P, p, h, S);
+  __syncthreads();
+  win_load_rows(S.Qs, P.qkv, P.ld, col0, S.qrow, NP);
+  win_load_rows(S.Ks, P.qkv + C, P.ld, col0, S.krow, NP);
+  win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.krow, NP);
+  win_load_rows(S.dOs, P.dO, P.ldo, col0, S.qrow, NP);
+  cp_commit();
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) lse_sm[i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] : INFINITY;
+  if (P.dtable != nullptr) {
+    float* z = (float*)priv;
+    const int nz = P.n_dq_warps * priv_stride / 4;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0.f;
+  }
+  cp_wait_all();
+  __syncthreads();
+  // delta_i = dO_i . O_i: dO from the staged tile, O rows straight from global; four lanes per row
+  for (int c = threadIdx.x; c < NP * 4; c += blockDim.x) {   // NP*4 is a multiple of 32: whole warps iterate
+    const int r = c >> 2, ch = c & 3;
+    const int gr = S.qrow[r];
+    uint4 o4 = make_uint4(0, 0, 0, 0);
+    if (gr >= 0) o4 = *(const uint4*)(P.O + (size_t)gr * P.ldo + col0 + ch * 8);
+    const uint4 a = *(const uint4*)(S.dOs + tile_off(r, ch));
+    const __nv_bfloat162* pa = (const __nv_bfloat162*)&a;
+    const __nv_bfloat162* po = (const __nv_bfloat162*)&o4;
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __bfloat1622float2(pa[j]), fo = __bfloat1622float2(po[j]);
+      d += fa.x * fo.x + fa.y * fo.y;
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    if (ch == 0) ndel_sm[r] = -d;
+  }
+  __syncthreads();
+  Lane L;
+  L.init();
+  const int nrb = NP >> 4;
+  const uint32_t lse_s = sm_addr(lse_sm), ndel_s = sm_addr(ndel_sm);
+  const int nq = P.n_dq_warps;
+  if (warp < nq) {
+    const uint32_t gtab_s = sm_addr(priv + warp * priv_stride);
+    const uint32_t stg_s = gtab_s + P.tab_stride;
+    if (masked) { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<true>(P, S, L, h, rb, lse_s, ndel_s, gtab_s, stg_s); }
+    else        { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<false>(P, S, L, h, rb, lse_s, ndel_s, gtab_s, stg_s); }
+  } else {
+    const int nk = nwarps - nq;
+    if (masked) { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<true>(P, S, L, h, jb, lse_s, ndel_s); }
+    else        { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<false>(P, S, L, h, jb, lse_s, ndel_s); }
+  }
+  if (P.dtable != nullptr) {
+    __syncthreads();
+    const int r0 = P.center - P.maxcode;
+    for (int r = threadIdx.x; r < P.n_used; r += blockDim.x) {
+      float acc = 0.f;
+      for (int w = 0; w < nq; ++w) acc += ((const float*)(priv + w * priv_stride))[r];
+      if (acc != 0.f) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], acc);
+    }
+  }
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int win_setup(WinParams& P, const WindowIndex& ix, int H, int hd, int& nthreads) {
+static constexpr size_t kSmemLimit = 227 * 1024;
+
+static void win_geometry(WinParams& P, const WindowIndex& ix, int H) {
   P.win = ix;
   P.heads = H;
   P.NP = (ix.N + 15) / 16 * 16;
@@ -582,51 +668,68 @@ static int win_setup(WinParams& P, const WindowIndex& ix, int H, int hd, int& nt
   P.center = (ix.WD - 1) * cH + (ix.WH - 1) * cW + (ix.WW - 1);
   P.maxcode = (ix.wd - 1) * cH + (ix.wh - 1) * cW + (ix.ww - 1);
   P.n_used = 2 * P.maxcode + 1;
-  const int nrb = P.NP / 16;
-  const int per = (nrb + 7) / 8;                 // row blocks per warp with at most 8 warps
-  const int nwarps = (nrb + per - 1) / per;
-  nthreads = nwarps * 32;
-  VALOR_REQUIRE(ix.N <= 4095 && 4 * (2 * P.maxcode + 1) < 65536, "window_attn: window too large for the packed tables");
-  (void)hd;
-  return 0;
+  P.tab_stride = (P.n_used * 4 + 15) / 16 * 16;
+}
+
+// forward: row blocks dealt round-robin to at most 8 warps
+static int fwd_warps(int nrb) {
+  const int per = (nrb + 7) / 8;
+  return (nrb + per - 1) / per;
+}
+
+// backward: split up to 14 warps between query blocks (dQ + bias gradient, ~1.35x the work of a key block) and key
+// blocks (dK, dV) so that the slower group finishes earliest; every dq warp needs a private table in shared memory
+static bool bwd_warps(int NP, int n_used, int& n_dq, int& n_dkv) {
+  const int nrb = NP / 16;
+  double best = 1e30;
+  n_dq = n_dkv = 0;
+  for (int q = 1; q <= 13; ++q)
+    for (int k = 1; q + k <= 14; ++k) {
+      if (win_smem_bytes(NP, n_used, true, q) > kSmemLimit) continue;
+      const double cost = std::max(1.35 * ((nrb + q - 1) / q), 1.0 * ((nrb + k - 1) / k)) + 1e-3 * (q + k);
+      if (cost < best) { best = cost; n_dq = q; n_dkv = k; }
+    }
+  return n_dq > 0;
 }
 
 bool window_cta_eligible(const WindowIndex& ix, int hd) {
-  const int NP = (ix.N + 15) / 16 * 16;
-  const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
-  const int n_used = 2 * ((ix.wd - 1) * cH + (ix.wh - 1) * cW + (ix.ww - 1)) + 1;
-  return hd == 32 && win_smem_bytes(32, NP, n_used, true) <= 227 * 1024;
+  if (hd != HD || ix.N > 4095) return false;
+  WinParams P = {};
+  win_geometry(P, ix, 1);
+  if (4 * (2 * P.maxcode + 1) >= 65536) return false;
+  if (ix.wh * ix.ww > 256 || ix.wd * ix.wh > 256) return false;   // small_div range
+  int q, k;
+  return win_smem_bytes(P.NP, P.n_used, false, 0) <= kSmemLimit && bwd_warps(P.NP, P.n_used, q, k);
 }
 
 int window_cta_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
                    int H, int hd, float scale, cudaStream_t st) {
+  VALOR_REQUIRE(hd == HD && H <= 65535, "window_cta_fwd: head dim 32 only");
   WinParams P = {};
-  int nthreads = 0;
-  if (win_setup(P, ix, H, hd, nthreads)) return 1;
+  win_geometry(P, ix, H);
   P.qkv = (const bf16*)qkv; P.ld = ld; P.O = (bf16*)O; P.ldo = ldo; P.lse = lse; P.scale = scale;
-  VALOR_REQUIRE(hd == 32 && H <= 65535, "window_cta_fwd: head dim 32 only");
-  const size_t smem = win_smem_bytes(32, P.NP, P.n_used, false);
-  auto kern = window_fwd_kernel<32>;
+  const size_t smem = win_smem_bytes(P.NP, P.n_used, false, 0);
   static size_t attr = 0;
-  if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  kern<<<dim3(Pn, H), nthreads, smem, st>>>(P);
+  if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  window_fwd_kernel<<<dim3(Pn, H), fwd_warps(P.NP / 16) * 32, smem, st>>>(P);
   return check_launch("window_fwd_kernel");
 }
 
 int window_cta_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
                    const float* lse, void* dqkv, long long lddqkv, float* dtable, int Pn, int H, int hd, float scale,
                    cudaStream_t st) {
+  VALOR_REQUIRE(hd == HD && H <= 65535, "window_cta_bwd: head dim 32 only");
   WinParams P = {};
-  int nthreads = 0;
-  if (win_setup(P, ix, H, hd, nthreads)) return 1;
+  win_geometry(P, ix, H);
   P.qkv = (const bf16*)qkv; P.ld = ld; P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.scale = scale;
   P.dO = (const bf16*)dO; P.dqkv = (bf16*)dqkv; P.lddqkv = lddqkv; P.dtable = dtable;
-  VALOR_REQUIRE(hd == 32 && H <= 65535, "window_cta_bwd: head dim 32 only");
-  const size_t smem = win_smem_bytes(32, P.NP, P.n_used, true);
-  auto kern = window_bwd_kernel<32>;
+  int n_dq = 0, n_dkv = 0;
+  VALOR_REQUIRE(bwd_warps(P.NP, P.n_used, n_dq, n_dkv), "window_cta_bwd: window does not fit in shared memory");
+  P.n_dq_warps = n_dq;
+  const size_t smem = win_smem_bytes(P.NP, P.n_used, true, n_dq);
   static size_t attr = 0;
-  if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  kern<<<dim3(Pn, H), nthreads, smem, st>>>(P);
+  if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  window_bwd_kernel<<<dim3(Pn, H), (n_dq + n_dkv) * 32, smem, st>>>(P);
   return check_launch("window_bwd_kernel");
 }
 
