@@ -130,8 +130,8 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float2 f = __bfloat1622float2(h[j]);
-        xg[2 * j] *= act_grad(f.x, VALOR_ACT_GELU);
-        xg[2 * j + 1] *= act_grad(f.y, VALOR_ACT_GELU);
+        xg[2 * j] *= gelu_grad_fast(f.x);
+        xg[2 * j + 1] *= gelu_grad_fast(f.y);
       }
     } else if (use_aux) {
       const int act = ep.act;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
       }
     } else if (MODE == EPI_GELU_PRE) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xg[j] = act_fwd(xg[j], VALOR_ACT_GELU);
+      for (int j = 0; j < 8; ++j) xg[j] = gelu_fwd_fast(xg[j]);
     } else if (MODE == EPI_GENERIC) {
       if (ep.act != VALOR_ACT_NONE) {
 #pragma unroll

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "attention.cuh"
 #include <algorithm>
+#include <utility>
 
 namespace valor {
 
@@ -199,7 +200,7 @@ static inline size_t win_smem_bytes(int NP, int n_used, bool bwd, int n_dq_warps
   b += (size_t)6 * NP * 4;                        // qrow krow qcode kcode qreg kreg
   const size_t tab = ((size_t)n_used * 4 + 15) / 16 * 16;
   b += tab;                                       // bias slice
-  if (bwd) b += (size_t)2 * NP * 4 + (size_t)n_dq_warps * (tab + 16 * 40 * 4);   // lse, -delta, per-warp tables + staging
+  if (bwd) b += (size_t)2 * NP * 4 + (size_t)n_dq_warps * (tab + 16 * 40 * 4 + 16);   // {lse, -delta}, per-warp tables + staging + parking word
   return b + 16;
 }
 
@@ -219,118 +220,163 @@ __device__ __forceinline__ Smem carve(unsigned char* smem, int NP, bool bwd) {
   return S;
 }
 
+// compile-time loop: the index arrives as std::integral_constant, so it can feed "n" asm operands
+template <int... I, class F>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+
+// [register + immediate] forms: one running per-lane base register serves a whole key / query sweep
+template <int OFF> __device__ __forceinline__ void ldsm4_o(uint32_t* r, uint32_t base) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4+%5];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(base), "n"(OFF));
+}
+template <int OFF> __device__ __forceinline__ void ldsm4t_o(uint32_t* r, uint32_t base) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4+%5];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(base), "n"(OFF));
+}
+template <int OFF> __device__ __forceinline__ uint2 ld_v2u32_o(uint32_t base) {
+  uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(base), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ float4 ld_v4f32_o(uint32_t base) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ uint32_t ldv_u32_o(uint32_t base) {
+  uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(base), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ float ldv_f32_o(uint32_t base) {
+  float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(base), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ void stv_v2f32_o(uint32_t base, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0+%1], {%2,%3};" ::"r"(base), "n"(OFF), "f"(x), "f"(y));
+}
+
 // ==========================================================================================
 // forward
 // ==========================================================================================
-// One 64-key block of one 16-query block.  TAIL: the block holds padding keys and fewer than four 16-key pairs.
+// Running state of one 16-query block while it sweeps the keys.
+struct FwdRow {
+  uint32_t qf[2][4];
+  uint32_t qaddr[2], qrg[2];
+  float o[5][4];       // o[4]: row sums (ones column)
+  float mref[2];       // the exponent reference; only moved when the block maximum outgrows it by kTau
+  uint32_t kb0, kb1;   // per-lane K fragment bases (ks = 0, 1), advanced 64 rows per block
+  uint32_t vt0, vt1;   // per-lane V^T fragment bases (dt = 0, 2)
+  uint32_t kc, kr;     // per-lane key code / region bases
+};
+constexpr float kTau = 8.0f;   // P <= e^8 between rescales: harmless in fp32 sums and bf16 P
+
+// One 64-key block.  TAIL: the block holds padding keys and fewer than four 16-key pairs.
 template <bool MASKED, bool TAIL>
-__device__ __forceinline__ void fwd_block(const Lane& L, uint32_t Kb, uint32_t Vb, uint32_t kcode_b, uint32_t kreg_b,
-                                          int keys_left, const uint32_t (&qf)[2][4], const uint32_t (&qaddr)[2],
-                                          const uint32_t (&qrg)[2], float scale, float (&o)[5][4], float (&mrow)[2]) {
+__device__ __forceinline__ void fwd_block(const Lane& L, FwdRow& R, int keys_left, float scale) {
   const int npair = TAIL ? min(4, (keys_left + 15) >> 4) : 4;
   float s[8][4];
-#pragma unroll
-  for (int pr = 0; pr < 4; ++pr)
+  static_for<4>([&](auto pr_) {
+    constexpr int pr = decltype(pr_)::value;
     if (!TAIL || pr < npair) {
       uint32_t b[4];
-      ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[0]);
-      mma_init(s[pr * 2], qf[0], b, 0.f, 0.f, 0.f, 0.f);
-      mma_init(s[pr * 2 + 1], qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
-      ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[1]);
-      mma_acc(s[pr * 2], qf[1], b);
-      mma_acc(s[pr * 2 + 1], qf[1], b + 2);
+      ldsm4_o<pr * 16 * ROWB>(b, R.kb0);
+      mma_init(s[pr * 2], R.qf[0], b, 0.f, 0.f, 0.f, 0.f);
+      mma_init(s[pr * 2 + 1], R.qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+      ldsm4_o<pr * 16 * ROWB>(b, R.kb1);
+      mma_acc(s[pr * 2], R.qf[1], b);
+      mma_acc(s[pr * 2 + 1], R.qf[1], b + 2);
     }
-  float mnew[2] = {mrow[0], mrow[1]};
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  });
+  float mblk[2] = {-INFINITY, -INFINITY};
+  static_for<8>([&](auto nt_) {
+    constexpr int nt = decltype(nt_)::value;
     if (!TAIL || (nt >> 1) < npair) {
-      const uint2 kc = ld_v2u32(kcode_b + 4u * (uint32_t)(nt * 8 + L.t4 * 2));
+      const uint2 kc = ld_v2u32_o<nt * 32>(R.kc);
       uint2 kr = make_uint2(0u, 0u);
-      if (MASKED) kr = ld_v2u32(kreg_b + 4u * (uint32_t)(nt * 8 + L.t4 * 2));
+      if (MASKED) kr = ld_v2u32_o<nt * 32>(R.kr);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = e >> 1;
-        float v = fmaf(s[nt][e], scale, ld_f32(qaddr[r] - ((e & 1) ? kc.y : kc.x)));
-        if (MASKED && qrg[r] != ((e & 1) ? kr.y : kr.x)) v += kMask;
+        float v = fmaf(s[nt][e], scale, ld_f32(R.qaddr[r] - ((e & 1) ? kc.y : kc.x)));
+        if (MASKED && R.qrg[r] != ((e & 1) ? kr.y : kr.x)) v += kMask;
         if (TAIL && nt * 8 + L.t4 * 2 + (e & 1) >= keys_left) v = -INFINITY;
         s[nt][e] = v;
-        mnew[r] = fmaxf(mnew[r], v);
+        mblk[r] = fmaxf(mblk[r], v);
       }
     }
+  });
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
-    mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
+    mblk[r] = fmaxf(mblk[r], __shfl_xor_sync(0xffffffffu, mblk[r], 1));
+    mblk[r] = fmaxf(mblk[r], __shfl_xor_sync(0xffffffffu, mblk[r], 2));
   }
-  float ml[2];
+  // lazy rescale: the running reference only follows the maximum when it has grown by more than kTau
+  if (__any_sync(0xffffffffu, mblk[0] > R.mref[0] + kTau || mblk[1] > R.mref[1] + kTau)) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {   // block 0 always holds real keys, so mnew is finite from the first block on
-    const float corr = ex2((mrow[r] - mnew[r]) * kLog2e);
-    mrow[r] = mnew[r];
-    ml[r] = -mnew[r] * kLog2e;
+    for (int r = 0; r < 2; ++r) {
+      const float mnew = fmaxf(R.mref[r], mblk[r]);     // finite: block 0 always holds real keys
+      const float corr = ex2((R.mref[r] - mnew) * kLog2e);
+      R.mref[r] = mnew;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { o[i][r * 2] *= corr; o[i][r * 2 + 1] *= corr; }
+      for (int i = 0; i < 5; ++i) { R.o[i][r * 2] *= corr; R.o[i][r * 2 + 1] *= corr; }
+    }
   }
+  const float ml[2] = {-R.mref[0] * kLog2e, -R.mref[1] * kLog2e};
   const uint32_t ones[2] = {0x3f803f80u, 0x3f803f80u};   // bf16 1.0 pairs: column block of ones -> row sums of P
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
+  static_for<4>([&](auto kk_) {
+    constexpr int kk = decltype(kk_)::value;
     if (!TAIL || kk < npair) {
       uint32_t pf[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int nt = kk * 2 + hf;
         float pv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) pv[e] = ex2(fmaf(s[nt][e], kLog2e, ml[e >> 1]));
+        for (int e = 0; e < 4; ++e) pv[e] = ex2(fmaf(s[kk * 2 + hf][e], kLog2e, ml[e >> 1]));
         pf[hf * 2 + 0] = pack2(pv[0], pv[1]);
         pf[hf * 2 + 1] = pack2(pv[2], pv[3]);
       }
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        uint32_t b[4];
-        ldsm4t(b, Vb + kk * 16 * ROWB + L.bt_off[ks]);
-        mma_acc(o[ks * 2], pf, b);
-        mma_acc(o[ks * 2 + 1], pf, b + 2);
-      }
-      mma_acc(o[4], pf, ones);
+      uint32_t b[4];
+      ldsm4t_o<kk * 16 * ROWB>(b, R.vt0);
+      mma_acc(R.o[0], pf, b);
+      mma_acc(R.o[1], pf, b + 2);
+      ldsm4t_o<kk * 16 * ROWB>(b, R.vt1);
+      mma_acc(R.o[2], pf, b);
+      mma_acc(R.o[3], pf, b + 2);
+      mma_acc(R.o[4], pf, ones);
     }
+  });
+  R.kb0 += 64 * ROWB; R.kb1 += 64 * ROWB; R.vt0 += 64 * ROWB; R.vt1 += 64 * ROWB; R.kc += 256; R.kr += 256;
 }
 
 template <bool MASKED>
 __device__ __forceinline__ void fwd_rows(const WinParams& P, const Smem& S, const Lane& L, int p, int h, int rb) {
   const int N = P.win.N;
   const uint32_t Qs = sm_addr(S.Qs), Ks = sm_addr(S.Ks), Vs = sm_addr(S.Vs);
-  const uint32_t tab_s = sm_addr(S.tab), kcode_s = sm_addr(S.kcode), kreg_s = sm_addr(S.kreg);
-  uint32_t qf[2][4];
-  ldsm4(qf[0], Qs + rb * 16 * ROWB + L.a_off[0]);
-  ldsm4(qf[1], Qs + rb * 16 * ROWB + L.a_off[1]);
+  const uint32_t tab_s = sm_addr(S.tab);
+  FwdRow R;
+  ldsm4(R.qf[0], Qs + rb * 16 * ROWB + L.a_off[0]);
+  ldsm4(R.qf[1], Qs + rb * 16 * ROWB + L.a_off[1]);
   const int i0 = rb * 16 + L.g;
-  const uint32_t qaddr[2] = {tab_s + S.qcode[i0], tab_s + S.qcode[i0 + 8]};
-  const uint32_t qrg[2] = {S.qreg[i0], S.qreg[i0 + 8]};
-  float o[5][4];
+  R.qaddr[0] = tab_s + S.qcode[i0]; R.qaddr[1] = tab_s + S.qcode[i0 + 8];
+  R.qrg[0] = S.qreg[i0]; R.qrg[1] = S.qreg[i0 + 8];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float mrow[2] = {-INFINITY, -INFINITY};
+  for (int i = 0; i < 5; ++i) R.o[i][0] = R.o[i][1] = R.o[i][2] = R.o[i][3] = 0.f;
+  R.mref[0] = R.mref[1] = -INFINITY;
+  R.kb0 = Ks + L.b_off[0]; R.kb1 = Ks + L.b_off[1];
+  R.vt0 = Vs + L.bt_off[0]; R.vt1 = Vs + L.bt_off[1];
+  R.kc = sm_addr(S.kcode) + L.t4 * 8; R.kr = sm_addr(S.kreg) + L.t4 * 8;
   const int nfull = N >> 6;
 #pragma unroll 1
-  for (int kb = 0; kb < nfull; ++kb)
-    fwd_block<MASKED, false>(L, Ks + kb * 64 * ROWB, Vs + kb * 64 * ROWB, kcode_s + kb * 256, kreg_s + kb * 256, 64, qf,
-                             qaddr, qrg, P.scale, o, mrow);
-  if (N & 63)
-    fwd_block<MASKED, true>(L, Ks + nfull * 64 * ROWB, Vs + nfull * 64 * ROWB, kcode_s + nfull * 256, kreg_s + nfull * 256,
-                            N - nfull * 64, qf, qaddr, qrg, P.scale, o, mrow);
+  for (int kb = 0; kb < nfull; ++kb) fwd_block<MASKED, false>(L, R, 64, P.scale);
+  if (N & 63) fwd_block<MASKED, true>(L, R, N - nfull * 64, P.scale);
   const int col0 = h * HD;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int i = i0 + r * 8;
     if (i < N) {
-      const float l = o[4][r * 2];   // every column of the ones block carries the row sum
+      const float l = R.o[4][r * 2];   // every column of the ones block carries the row sum
       const float inv = 1.f / l;
       bf16* dst = P.O + (size_t)S.qrow[i] * P.ldo + col0;
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt)
-        *(uint32_t*)(dst + dt * 8 + L.t4 * 2) = pack2(o[dt][r * 2] * inv, o[dt][r * 2 + 1] * inv);
-      if (L.t4 == 0) P.lse[((size_t)p * P.heads + h) * N + i] = mrow[r] + log2f(l) * kLn2;
+        *(uint32_t*)(dst + dt * 8 + L.t4 * 2) = pack2(R.o[dt][r * 2] * inv, R.o[dt][r * 2 + 1] * inv);
+      if (L.t4 == 0) P.lse[((size_t)p * P.heads + h) * N + i] = R.mref[r] + log2f(l) * kLn2;
     }
   }
 }
@@ -363,106 +409,149 @@ window_fwd_kernel(WinParams P) {
 // ==========================================================================================
 // backward
 // ==========================================================================================
-// dQ for one 16-query block; the block's dS also goes into this warp's private bias-gradient table.
+// Running state of one 16-query block (dQ + bias gradient) while it sweeps the keys.
+struct DqRow {
+  uint32_t qf[2][4], dof[2][4];
+  uint32_t qaddr[2], qrg[2];
+  float nlse[2], ndel[2];
+  float dq[4][4];
+  uint32_t kb0, kb1, vb0, vb1;   // per-lane K / V fragment bases (ks = 0, 1)
+  uint32_t kt0, kt1;             // per-lane K^T fragment bases (dt = 0, 2)
+  uint32_t kc, kr;               // per-lane key code / region bases (fragment columns)
+  uint32_t kcl;                  // code-word address of key (k0 + lane): the fold's column owner
+  uint32_t my_qcode;             // qcode of row (lane & 15) of the block
+  uint32_t gtab, stg_w, stg_r, dummy;   // private table, staging bases (fragment layout / lane layout), parking word
+  __device__ __forceinline__ void advance(int keys) {
+    kb0 += keys * ROWB; kb1 += keys * ROWB; vb0 += keys * ROWB; vb1 += keys * ROWB; kt0 += keys * ROWB; kt1 += keys * ROWB;
+    kc += keys * 4; kr += keys * 4; kcl += keys * 4;
+  }
+};
+
+// One 32-key sweep; SUB selects the first / second half of an unrolled pair (immediate offsets).
+template <bool MASKED, bool TAIL, int SUB>
+__device__ __forceinline__ void dq_sweep(const Lane& L, DqRow& R, int left, float scale, bool want_dtab) {
+  constexpr int KO = SUB * 32 * ROWB;   // byte offset of this sweep inside the pair
+  constexpr int CO = SUB * 128;         // code-word offset
+  const int npair = TAIL ? min(2, (left + 15) >> 4) : 2;
+  float s[4][4], dp[4][4];
+  static_for<2>([&](auto pr_) {
+    constexpr int pr = decltype(pr_)::value;
+    if (!TAIL || pr < npair) {
+      uint32_t b[4];
+      ldsm4_o<KO + pr * 16 * ROWB>(b, R.kb0);
+      mma_init(s[pr * 2], R.qf[0], b, 0.f, 0.f, 0.f, 0.f);
+      mma_init(s[pr * 2 + 1], R.qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+      ldsm4_o<KO + pr * 16 * ROWB>(b, R.kb1);
+      mma_acc(s[pr * 2], R.qf[1], b);
+      mma_acc(s[pr * 2 + 1], R.qf[1], b + 2);
+      ldsm4_o<KO + pr * 16 * ROWB>(b, R.vb0);   // dP - delta: the accumulator starts at -delta_i
+      mma_init(dp[pr * 2], R.dof[0], b, R.ndel[0], R.ndel[0], R.ndel[1], R.ndel[1]);
+      mma_init(dp[pr * 2 + 1], R.dof[0], b + 2, R.ndel[0], R.ndel[0], R.ndel[1], R.ndel[1]);
+      ldsm4_o<KO + pr * 16 * ROWB>(b, R.vb1);
+      mma_acc(dp[pr * 2], R.dof[1], b);
+      mma_acc(dp[pr * 2 + 1], R.dof[1], b + 2);
+    }
+  });
+  uint32_t dsf[2][4];
+  static_for<4>([&](auto nt_) {
+    constexpr int nt = decltype(nt_)::value;
+    float ds[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!TAIL || (nt >> 1) < npair) {
+      const uint2 kc = ld_v2u32_o<CO + nt * 32>(R.kc);
+      uint2 kr = make_uint2(0u, 0u);
+      if (MASKED) kr = ld_v2u32_o<CO + nt * 32>(R.kr);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        float v = fmaf(s[nt][e], scale, ld_f32(R.qaddr[r] - ((e & 1) ? kc.y : kc.x)));
+        if (MASKED && R.qrg[r] != ((e & 1) ? kr.y : kr.x)) v += kMask;
+        float pr_ = ex2(fmaf(v, kLog2e, R.nlse[r]));
+        if (TAIL && nt * 8 + L.t4 * 2 + (e & 1) >= left) pr_ = 0.f;   // padding key
+        ds[e] = pr_ * dp[nt][e];
+      }
+    }
+    if (want_dtab) {   // stage the fp32 tile [16 rows][32 keys], row pitch 40 floats
+      stv_v2f32_o<nt * 32>(R.stg_w, ds[0], ds[1]);
+      stv_v2f32_o<8 * 160 + nt * 32>(R.stg_w, ds[2], ds[3]);
+    }
+    dsf[nt >> 1][(nt & 1) * 2 + 0] = pack2(ds[0], ds[1]);
+    dsf[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
+  });
+  static_for<2>([&](auto kk_) {
+    constexpr int kk = decltype(kk_)::value;
+    if (!TAIL || kk < npair) {
+      uint32_t b[4];
+      ldsm4t_o<KO + kk * 16 * ROWB>(b, R.kt0);
+      mma_acc(R.dq[0], dsf[kk], b);
+      mma_acc(R.dq[1], dsf[kk], b + 2);
+      ldsm4t_o<KO + kk * 16 * ROWB>(b, R.kt1);
+      mma_acc(R.dq[2], dsf[kk], b);
+      mma_acc(R.dq[3], dsf[kk], b + 2);
+    }
+  });
+  if (want_dtab) {
+    // Fold the staged tile into the private table, one query row per step: lane l owns key k0 + l.  Within a row
+    // distinct keys hit distinct slots; the warp is converged and its shared-memory instructions retire in
+    // program order, so row r+1 observes row r's stores.  Padding keys (tail only) are parked on a dummy word.
+    __syncwarp();
+    const uint32_t base_l = R.gtab - ldv_u32_o<CO>(R.kcl);
+    const bool live = !TAIL || L.lane < left;
+    static_for<16>([&](auto r_) {
+      constexpr int r = decltype(r_)::value;
+      uint32_t slot = base_l + __shfl_sync(0xffffffffu, R.my_qcode, r);
+      if (TAIL) slot = live ? slot : R.dummy;
+      const float add = ldv_f32_o<r * 160>(R.stg_r);
+      stv_f32(slot, ldv_f32(slot) + add);
+    });
+    __syncwarp();
+  }
+}
+
 template <bool MASKED>
-__device__ __forceinline__ void bwd_dq_unit(const WinParams& P, const Smem& S, const Lane& L, int h, int rb, uint32_t lse_s,
-                                            uint32_t ndel_s, uint32_t gtab_s, uint32_t stg_s) {
+__device__ __forceinline__ void bwd_dq_unit(const WinParams& P, const Smem& S, const Lane& L, int h, int rb, uint32_t ln_s,
+                                            uint32_t gtab_s, uint32_t stg_s) {
   const int N = P.win.N;
   const uint32_t Qs = sm_addr(S.Qs), Ks = sm_addr(S.Ks), Vs = sm_addr(S.Vs), dOs = sm_addr(S.dOs);
-  const uint32_t tab_s = sm_addr(S.tab), kcode_s = sm_addr(S.kcode), kreg_s = sm_addr(S.kreg);
-  uint32_t qf[2][4], dof[2][4];
+  const uint32_t tab_s = sm_addr(S.tab);
+  DqRow R;
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    ldsm4(qf[ks], Qs + rb * 16 * ROWB + L.a_off[ks]);
-    ldsm4(dof[ks], dOs + rb * 16 * ROWB + L.a_off[ks]);
+    ldsm4(R.qf[ks], Qs + rb * 16 * ROWB + L.a_off[ks]);
+    ldsm4(R.dof[ks], dOs + rb * 16 * ROWB + L.a_off[ks]);
   }
   const int i0 = rb * 16 + L.g;
-  const uint32_t qaddr[2] = {tab_s + S.qcode[i0], tab_s + S.qcode[i0 + 8]};
-  const uint32_t qrg[2] = {S.qreg[i0], S.qreg[i0 + 8]};
-  const float nlse[2] = {-ld_f32(lse_s + 4u * i0) * kLog2e, -ld_f32(lse_s + 4u * (i0 + 8)) * kLog2e};   // -inf on padding rows
-  const float ndel[2] = {ld_f32(ndel_s + 4u * i0), ld_f32(ndel_s + 4u * (i0 + 8))};
-  // row r of the block is folded into the gradient table at byte offset qcode(row r) - kcode(key)
-  const uint32_t my_qcode = S.qcode[rb * 16 + (L.lane & 15)];
-  const bool want_dtab = P.dtable != nullptr;
-  float dq[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-  const int nsweep = (N + 31) >> 5;
-#pragma unroll 1
-  for (int hb = 0; hb < nsweep; ++hb) {
-    const int k0 = hb * 32;
-    const int left = N - k0;                        // real keys from k0 on
-    const int npair = min(2, (left + 15) >> 4);
-    const uint32_t Kb = Ks + k0 * ROWB, Vb = Vs + k0 * ROWB;
-    float s[4][4], dp[4][4];
-#pragma unroll
-    for (int pr = 0; pr < 2; ++pr)
-      if (pr < npair) {
-        uint32_t b[4];
-        ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[0]);
-        mma_init(s[pr * 2], qf[0], b, 0.f, 0.f, 0.f, 0.f);
-        mma_init(s[pr * 2 + 1], qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
-        ldsm4(b, Kb + pr * 16 * ROWB + L.b_off[1]);
-        mma_acc(s[pr * 2], qf[1], b);
-        mma_acc(s[pr * 2 + 1], qf[1], b + 2);
-        ldsm4(b, Vb + pr * 16 * ROWB + L.b_off[0]);   // dP - delta: the accumulator starts at -delta_i
-        mma_init(dp[pr * 2], dof[0], b, ndel[0], ndel[0], ndel[1], ndel[1]);
-        mma_init(dp[pr * 2 + 1], dof[0], b + 2, ndel[0], ndel[0], ndel[1], ndel[1]);
-        ldsm4(b, Vb + pr * 16 * ROWB + L.b_off[1]);
-        mma_acc(dp[pr * 2], dof[1], b);
-        mma_acc(dp[pr * 2 + 1], dof[1], b + 2);
-      }
-    uint32_t dsf[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float ds[4] = {0.f, 0.f, 0.f, 0.f};
-      if ((nt >> 1) < npair) {
-        const uint2 kc = ld_v2u32(kcode_s + 4u * (uint32_t)(k0 + nt * 8 + L.t4 * 2));
-        uint2 kr = make_uint2(0u, 0u);
-        if (MASKED) kr = ld_v2u32(kreg_s + 4u * (uint32_t)(k0 + nt * 8 + L.t4 * 2));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = e >> 1;
-          float v = fmaf(s[nt][e], P.scale, ld_f32(qaddr[r] - ((e & 1) ? kc.y : kc.x)));
-          if (MASKED && qrg[r] != ((e & 1) ? kr.y : kr.x)) v += kMask;
-          float pr_ = ex2(fmaf(v, kLog2e, nlse[r]));
-          if (nt * 8 + L.t4 * 2 + (e & 1) >= left) pr_ = 0.f;   // padding key (only ever true in the last sweep)
-          ds[e] = pr_ * dp[nt][e];
-        }
-      }
-      if (want_dtab) {   // stage the fp32 tile [16 rows][32 keys], row pitch 40 floats
-        stv_v2f32(stg_s + 4u * (uint32_t)(L.g * 40 + nt * 8 + L.t4 * 2), ds[0], ds[1]);
-        stv_v2f32(stg_s + 4u * (uint32_t)((L.g + 8) * 40 + nt * 8 + L.t4 * 2), ds[2], ds[3]);
-      }
-      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack2(ds[0], ds[1]);
-      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk)
-      if (kk < npair) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t b[4];
-          ldsm4t(b, Kb + kk * 16 * ROWB + L.bt_off[ks]);
-          mma_acc(dq[ks * 2], dsf[kk], b);
-          mma_acc(dq[ks * 2 + 1], dsf[kk], b + 2);
-        }
-      }
-    if (want_dtab) {
-      // fold the staged tile into the private table, one query row per step: lane l owns key k0 + l, and
-      // within a row distinct keys hit distinct slots
-      __syncwarp();
-      const bool live = L.lane < left;
-      const uint32_t kc_l = S.kcode[min(k0 + L.lane, P.NP - 1)];
-#pragma unroll 4
-      for (int r = 0; r < 16; ++r) {
-        const uint32_t slot = gtab_s + __shfl_sync(0xffffffffu, my_qcode, r) - kc_l;
-        const float add = ldv_f32(stg_s + 4u * (uint32_t)(r * 40 + L.lane));
-        if (live) stv_f32(slot, ldv_f32(slot) + add);
-        __syncwarp();
-      }
-    }
+  R.qaddr[0] = tab_s + S.qcode[i0]; R.qaddr[1] = tab_s + S.qcode[i0 + 8];
+  R.qrg[0] = S.qreg[i0]; R.qrg[1] = S.qreg[i0 + 8];
+  {
+    const float2 a = ld_v2f32(ln_s + 8u * i0), b = ld_v2f32(ln_s + 8u * (i0 + 8));   // {lse, -delta}
+    R.nlse[0] = -a.x * kLog2e; R.nlse[1] = -b.x * kLog2e;                              // -inf on padding rows -> p = 0
+    R.ndel[0] = a.y; R.ndel[1] = b.y;
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) R.dq[i][0] = R.dq[i][1] = R.dq[i][2] = R.dq[i][3] = 0.f;
+  R.kb0 = Ks + L.b_off[0]; R.kb1 = Ks + L.b_off[1]; R.vb0 = Vs + L.b_off[0]; R.vb1 = Vs + L.b_off[1];
+  R.kt0 = Ks + L.bt_off[0]; R.kt1 = Ks + L.bt_off[1];
+  R.kc = sm_addr(S.kcode) + L.t4 * 8; R.kr = sm_addr(S.kreg) + L.t4 * 8;
+  R.kcl = sm_addr(S.kcode) + L.lane * 4;
+  R.my_qcode = S.qcode[rb * 16 + (L.lane & 15)];
+  R.gtab = gtab_s;
+  R.stg_w = stg_s + 4u * (uint32_t)(L.g * 40 + L.t4 * 2);
+  R.stg_r = stg_s + 4u * (uint32_t)L.lane;
+  R.dummy = stg_s + 16 * 40 * 4;
+  const bool want_dtab = P.dtable != nullptr;
+  const int nfull = N >> 5;
+  int hb = 0;
+#pragma unroll 1
+  for (; hb + 2 <= nfull; hb += 2) {
+    dq_sweep<MASKED, false, 0>(L, R, 32, P.scale, want_dtab);
+    dq_sweep<MASKED, false, 1>(L, R, 32, P.scale, want_dtab);
+    R.advance(64);
+  }
+  if (hb < nfull) {
+    dq_sweep<MASKED, false, 0>(L, R, 32, P.scale, want_dtab);
+    R.advance(32);
+  }
+  if (N & 31) dq_sweep<MASKED, true, 0>(L, R, N & 31, P.scale, want_dtab);
   const int col0 = h * HD;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -471,98 +560,132 @@ __device__ __forceinline__ void bwd_dq_unit(const WinParams& P, const Smem& S, c
       bf16* dst = P.dqkv + (size_t)S.qrow[i] * P.lddqkv + col0;
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt)
-        *(uint32_t*)(dst + dt * 8 + L.t4 * 2) = pack2(dq[dt][r * 2] * P.scale, dq[dt][r * 2 + 1] * P.scale);
+        *(uint32_t*)(dst + dt * 8 + L.t4 * 2) = pack2(R.dq[dt][r * 2] * P.scale, R.dq[dt][r * 2 + 1] * P.scale);
     }
   }
 }
 
-// dK, dV for one 16-key block.
+// dK, dV for one 16-key block: running state while it sweeps the queries.
+struct DkvRow {
+  uint32_t kf[2][4], vf[2][4];
+  uint32_t kaddr[2], krg[2];
+  float dk[4][4], dv[4][4];
+  uint32_t qb0, qb1, dob0, dob1;   // per-lane Q / dO fragment bases (ks = 0, 1)
+  uint32_t qt0, qt1, dot0, dot1;   // per-lane Q^T / dO^T fragment bases (dt = 0, 2)
+  uint32_t qc, qr, ln;             // per-lane query code / region / {lse, -delta} bases (fragment columns)
+  __device__ __forceinline__ void advance(int rows) {
+    qb0 += rows * ROWB; qb1 += rows * ROWB; dob0 += rows * ROWB; dob1 += rows * ROWB;
+    qt0 += rows * ROWB; qt1 += rows * ROWB; dot0 += rows * ROWB; dot1 += rows * ROWB;
+    qc += rows * 4; qr += rows * 4; ln += rows * 8;
+  }
+};
+
+template <bool MASKED, bool TAIL, int SUB>
+__device__ __forceinline__ void dkv_sweep(const Lane& L, DkvRow& R, int left, float scale) {
+  constexpr int QO = SUB * 32 * ROWB;
+  constexpr int CO = SUB * 128;
+  constexpr int LO = SUB * 256;
+  const int npair = TAIL ? min(2, (left + 15) >> 4) : 2;
+  float s[4][4], dp[4][4];   // rows = keys (g, g+8), cols = queries
+  static_for<2>([&](auto pr_) {
+    constexpr int pr = decltype(pr_)::value;
+    if (!TAIL || pr < npair) {
+      uint32_t b[4];
+      const float4 l0 = ld_v4f32_o<LO + pr * 128>(R.ln);        // {lse, -delta} of the two query columns, n-tile 2*pr
+      const float4 l1 = ld_v4f32_o<LO + pr * 128 + 64>(R.ln);   // n-tile 2*pr + 1
+      ldsm4_o<QO + pr * 16 * ROWB>(b, R.qb0);
+      mma_init(s[pr * 2], R.kf[0], b, 0.f, 0.f, 0.f, 0.f);
+      mma_init(s[pr * 2 + 1], R.kf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+      ldsm4_o<QO + pr * 16 * ROWB>(b, R.qb1);
+      mma_acc(s[pr * 2], R.kf[1], b);
+      mma_acc(s[pr * 2 + 1], R.kf[1], b + 2);
+      ldsm4_o<QO + pr * 16 * ROWB>(b, R.dob0);
+      mma_init(dp[pr * 2], R.vf[0], b, l0.y, l0.w, l0.y, l0.w);
+      mma_init(dp[pr * 2 + 1], R.vf[0], b + 2, l1.y, l1.w, l1.y, l1.w);
+      ldsm4_o<QO + pr * 16 * ROWB>(b, R.dob1);
+      mma_acc(dp[pr * 2], R.vf[1], b);
+      mma_acc(dp[pr * 2 + 1], R.vf[1], b + 2);
+    }
+  });
+  uint32_t pf[2][4], dsf[2][4];
+  static_for<4>([&](auto nt_) {
+    constexpr int nt = decltype(nt_)::value;
+    float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!TAIL || (nt >> 1) < npair) {
+      const uint2 qc = ld_v2u32_o<CO + nt * 32>(R.qc);       // two consecutive queries (columns of S^T)
+      const float4 l4 = ld_v4f32_o<LO + nt * 64>(R.ln);      // lse = +inf on padding queries -> p = 0
+      uint2 qr = make_uint2(0u, 0u);
+      if (MASKED) qr = ld_v2u32_o<CO + nt * 32>(R.qr);
+      const float nl[2] = {-l4.x * kLog2e, -l4.z * kLog2e};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        float v = fmaf(s[nt][e], scale, ld_f32(R.kaddr[r] + ((e & 1) ? qc.y : qc.x)));
+        if (MASKED && R.krg[r] != ((e & 1) ? qr.y : qr.x)) v += kMask;
+        const float pr_ = ex2(fmaf(v, kLog2e, nl[e & 1]));
+        pv[e] = pr_;
+        ds[e] = pr_ * dp[nt][e];
+      }
+    }
+    pf[nt >> 1][(nt & 1) * 2 + 0] = pack2(pv[0], pv[1]);
+    pf[nt >> 1][(nt & 1) * 2 + 1] = pack2(pv[2], pv[3]);
+    dsf[nt >> 1][(nt & 1) * 2 + 0] = pack2(ds[0], ds[1]);
+    dsf[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
+  });
+  static_for<2>([&](auto kk_) {   // contraction over the 16-query pairs of this sweep
+    constexpr int kk = decltype(kk_)::value;
+    if (!TAIL || kk < npair) {
+      uint32_t b[4];
+      ldsm4t_o<QO + kk * 16 * ROWB>(b, R.dot0);
+      mma_acc(R.dv[0], pf[kk], b);
+      mma_acc(R.dv[1], pf[kk], b + 2);
+      ldsm4t_o<QO + kk * 16 * ROWB>(b, R.dot1);
+      mma_acc(R.dv[2], pf[kk], b);
+      mma_acc(R.dv[3], pf[kk], b + 2);
+      ldsm4t_o<QO + kk * 16 * ROWB>(b, R.qt0);
+      mma_acc(R.dk[0], dsf[kk], b);
+      mma_acc(R.dk[1], dsf[kk], b + 2);
+      ldsm4t_o<QO + kk * 16 * ROWB>(b, R.qt1);
+      mma_acc(R.dk[2], dsf[kk], b);
+      mma_acc(R.dk[3], dsf[kk], b + 2);
+    }
+  });
+}
+
 template <bool MASKED>
-__device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, const Lane& L, int h, int jb, uint32_t lse_s,
-                                             uint32_t ndel_s) {
+__device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, const Lane& L, int h, int jb, uint32_t ln_s) {
   const int N = P.win.N;
   const uint32_t Qs = sm_addr(S.Qs), Ks = sm_addr(S.Ks), Vs = sm_addr(S.Vs), dOs = sm_addr(S.dOs);
-  const uint32_t tab_s = sm_addr(S.tab), qcode_s = sm_addr(S.qcode), qreg_s = sm_addr(S.qreg);
-  uint32_t kf[2][4], vf[2][4];
+  const uint32_t tab_s = sm_addr(S.tab);
+  DkvRow R;
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    ldsm4(kf[ks], Ks + jb * 16 * ROWB + L.a_off[ks]);
-    ldsm4(vf[ks], Vs + jb * 16 * ROWB + L.a_off[ks]);
+    ldsm4(R.kf[ks], Ks + jb * 16 * ROWB + L.a_off[ks]);
+    ldsm4(R.vf[ks], Vs + jb * 16 * ROWB + L.a_off[ks]);
   }
   const int j0 = jb * 16 + L.g;   // keys j0, j0+8 (padding keys: K/V rows are zero, results dropped)
-  const uint32_t kaddr[2] = {tab_s - S.kcode[j0], tab_s - S.kcode[j0 + 8]};
-  const uint32_t krg[2] = {S.kreg[j0], S.kreg[j0 + 8]};
-  float dk[4][4], dv[4][4];
+  R.kaddr[0] = tab_s - S.kcode[j0]; R.kaddr[1] = tab_s - S.kcode[j0 + 8];
+  R.krg[0] = S.kreg[j0]; R.krg[1] = S.kreg[j0 + 8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
-  const int nsweep = (N + 31) >> 5;
+    for (int e = 0; e < 4; ++e) R.dk[i][e] = R.dv[i][e] = 0.f;
+  R.qb0 = Qs + L.b_off[0]; R.qb1 = Qs + L.b_off[1]; R.dob0 = dOs + L.b_off[0]; R.dob1 = dOs + L.b_off[1];
+  R.qt0 = Qs + L.bt_off[0]; R.qt1 = Qs + L.bt_off[1]; R.dot0 = dOs + L.bt_off[0]; R.dot1 = dOs + L.bt_off[1];
+  R.qc = sm_addr(S.qcode) + L.t4 * 8; R.qr = sm_addr(S.qreg) + L.t4 * 8; R.ln = ln_s + L.t4 * 16;
+  const int nfull = N >> 5;
+  int hb = 0;
 #pragma unroll 1
-  for (int hb = 0; hb < nsweep; ++hb) {
-    const int q0 = hb * 32;
-    const int npair = min(2, (N - q0 + 15) >> 4);
-    const uint32_t Qb = Qs + q0 * ROWB, dOb = dOs + q0 * ROWB;
-    float s[4][4], dp[4][4];   // rows = keys (g, g+8), cols = queries
-#pragma unroll
-    for (int pr = 0; pr < 2; ++pr)
-      if (pr < npair) {
-        uint32_t b[4];
-        const float2 nd0 = ld_v2f32(ndel_s + 4u * (uint32_t)(q0 + pr * 16 + L.t4 * 2));       // -delta of the two query columns
-        const float2 nd1 = ld_v2f32(ndel_s + 4u * (uint32_t)(q0 + pr * 16 + 8 + L.t4 * 2));
-        ldsm4(b, Qb + pr * 16 * ROWB + L.b_off[0]);
-        mma_init(s[pr * 2], kf[0], b, 0.f, 0.f, 0.f, 0.f);
-        mma_init(s[pr * 2 + 1], kf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
-        ldsm4(b, Qb + pr * 16 * ROWB + L.b_off[1]);
-        mma_acc(s[pr * 2], kf[1], b);
-        mma_acc(s[pr * 2 + 1], kf[1], b + 2);
-        ldsm4(b, dOb + pr * 16 * ROWB + L.b_off[0]);
-        mma_init(dp[pr * 2], vf[0], b, nd0.x, nd0.y, nd0.x, nd0.y);
-        mma_init(dp[pr * 2 + 1], vf[0], b + 2, nd1.x, nd1.y, nd1.x, nd1.y);
-        ldsm4(b, dOb + pr * 16 * ROWB + L.b_off[1]);
-        mma_acc(dp[pr * 2], vf[1], b);
-        mma_acc(dp[pr * 2 + 1], vf[1], b + 2);
-      }
-    uint32_t pf[2][4], dsf[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
-      if ((nt >> 1) < npair) {
-        const uint32_t ib = (uint32_t)(q0 + nt * 8 + L.t4 * 2);   // two consecutive queries (columns of S^T)
-        const uint2 qc = ld_v2u32(qcode_s + 4u * ib);
-        const float2 l2 = ld_v2f32(lse_s + 4u * ib);              // +inf on padding queries -> p = 0
-        uint2 qr = make_uint2(0u, 0u);
-        if (MASKED) qr = ld_v2u32(qreg_s + 4u * ib);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = e >> 1;
-          float v = fmaf(s[nt][e], P.scale, ld_f32(kaddr[r] + ((e & 1) ? qc.y : qc.x)));
-          if (MASKED && krg[r] != ((e & 1) ? qr.y : qr.x)) v += kMask;
-          const float pr_ = ex2((v - ((e & 1) ? l2.y : l2.x)) * kLog2e);
-          pv[e] = pr_;
-          ds[e] = pr_ * dp[nt][e];
-        }
-      }
-      pf[nt >> 1][(nt & 1) * 2 + 0] = pack2(pv[0], pv[1]);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack2(pv[2], pv[3]);
-      dsf[nt >> 1][(nt & 1) * 2 + 0] = pack2(ds[0], ds[1]);
-      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack2(ds[2], ds[3]);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk)   // contraction over the 16-query pairs of this sweep
-      if (kk < npair) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t b[4];
-          ldsm4t(b, dOb + kk * 16 * ROWB + L.bt_off[ks]);
-          mma_acc(dv[ks * 2], pf[kk], b);
-          mma_acc(dv[ks * 2 + 1], pf[kk], b + 2);
-          ldsm4t(b, Qb + kk * 16 * ROWB + L.bt_off[ks]);
-          mma_acc(dk[ks * 2], dsf[kk], b);
-          mma_acc(dk[ks * 2 + 1], dsf[kk], b + 2);
-        }
-      }
+  for (; hb + 2 <= nfull; hb += 2) {
+    dkv_sweep<MASKED, false, 0>(L, R, 32, P.scale);
+    dkv_sweep<MASKED, false, 1>(L, R, 32, P.scale);
+    R.advance(64);
   }
+  if (hb < nfull) {
+    dkv_sweep<MASKED, false, 0>(L, R, 32, P.scale);
+    R.advance(32);
+  }
+  if (N & 31) dkv_sweep<MASKED, true, 0>(L, R, N & 31, P.scale);
   const int C = P.heads * HD, col0 = h * HD;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -572,22 +695,21 @@ __device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, 
       bf16* dstv = dstk + C;
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt) {
-        *(uint32_t*)(dstk + dt * 8 + L.t4 * 2) = pack2(dk[dt][r * 2] * P.scale, dk[dt][r * 2 + 1] * P.scale);
-        *(uint32_t*)(dstv + dt * 8 + L.t4 * 2) = pack2(dv[dt][r * 2], dv[dt][r * 2 + 1]);
+        *(uint32_t*)(dstk + dt * 8 + L.t4 * 2) = pack2(R.dk[dt][r * 2] * P.scale, R.dk[dt][r * 2 + 1] * P.scale);
+        *(uint32_t*)(dstv + dt * 8 + L.t4 * 2) = pack2(R.dv[dt][r * 2], R.dv[dt][r * 2 + 1]);
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(384, 1)
 window_bwd_kernel(WinParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int NP = P.NP;
   const Smem S = carve(smem, NP, true);
-  float* lse_sm = (float*)((unsigned char*)S.tab + P.tab_stride);   // natural-log lse; +inf on padding rows
-  float* ndel_sm = lse_sm + NP;                                      // -delta_i
-  unsigned char* priv = (unsigned char*)(ndel_sm + NP);              // per dq warp: [tab_stride] table + [16][40] staging
-  const int priv_stride = P.tab_stride + 16 * 40 * 4;
+  float* ln_sm = (float*)((unsigned char*)S.tab + P.tab_stride);    // per query {natural-log lse (+inf on padding), -delta}
+  unsigned char* priv = (unsigned char*)(ln_sm + 2 * NP);            // per dq warp: [tab_stride] table + [16][40] staging + parking word
+  const int priv_stride = P.tab_stride + 16 * 40 * 4 + 16;
   const int p = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int C = P.heads * HD, col0 = h * HD;
@@ -599,7 +721,7 @@ window_bwd_kernel(WinParams P) {
   win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.krow, NP);
   win_load_rows(S.dOs, P.dO, P.ldo, col0, S.qrow, NP);
   cp_commit();
-  for (int i = threadIdx.x; i < NP; i += blockDim.x) lse_sm[i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] : INFINITY;
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) ln_sm[2 * i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] : INFINITY;
   if (P.dtable != nullptr) {
     float* z = (float*)priv;
     const int nz = P.n_dq_warps * priv_stride / 4;
@@ -624,23 +746,23 @@ window_bwd_kernel(WinParams P) {
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
-    if (ch == 0) ndel_sm[r] = -d;
+    if (ch == 0) ln_sm[2 * r + 1] = -d;
   }
   __syncthreads();
   Lane L;
   L.init();
   const int nrb = NP >> 4;
-  const uint32_t lse_s = sm_addr(lse_sm), ndel_s = sm_addr(ndel_sm);
+  const uint32_t ln_s = sm_addr(ln_sm);
   const int nq = P.n_dq_warps;
   if (warp < nq) {
     const uint32_t gtab_s = sm_addr(priv + warp * priv_stride);
     const uint32_t stg_s = gtab_s + P.tab_stride;
-    if (masked) { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<true>(P, S, L, h, rb, lse_s, ndel_s, gtab_s, stg_s); }
-    else        { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<false>(P, S, L, h, rb, lse_s, ndel_s, gtab_s, stg_s); }
+    if (masked) { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<true>(P, S, L, h, rb, ln_s, gtab_s, stg_s); }
+    else        { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<false>(P, S, L, h, rb, ln_s, gtab_s, stg_s); }
   } else {
     const int nk = nwarps - nq;
-    if (masked) { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<true>(P, S, L, h, jb, lse_s, ndel_s); }
-    else        { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<false>(P, S, L, h, jb, lse_s, ndel_s); }
+    if (masked) { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<true>(P, S, L, h, jb, ln_s); }
+    else        { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<false>(P, S, L, h, jb, ln_s); }
   }
   if (P.dtable != nullptr) {
     __syncthreads();
@@ -677,14 +799,14 @@ static int fwd_warps(int nrb) {
   return (nrb + per - 1) / per;
 }
 
-// backward: split up to 14 warps between query blocks (dQ + bias gradient, ~1.35x the work of a key block) and key
+// backward: split up to 12 warps between query blocks (dQ + bias gradient, ~1.35x the work of a key block) and key
 // blocks (dK, dV) so that the slower group finishes earliest; every dq warp needs a private table in shared memory
 static bool bwd_warps(int NP, int n_used, int& n_dq, int& n_dkv) {
   const int nrb = NP / 16;
   double best = 1e30;
   n_dq = n_dkv = 0;
   for (int q = 1; q <= 13; ++q)
-    for (int k = 1; q + k <= 14; ++k) {
+    for (int k = 1; q + k <= 12; ++k) {
       if (win_smem_bytes(NP, n_used, true, q) > kSmemLimit) continue;
       const double cost = std::max(1.35 * ((nrb + q - 1) / q), 1.0 * ((nrb + k - 1) / k)) + 1e-3 * (q + k);
       if (cost < best) { best = cost; n_dq = q; n_dkv = k; }
