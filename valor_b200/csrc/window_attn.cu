@@ -12,8 +12,8 @@
 //             16-key blocks (S^T = K.Q^T so P^T / dS^T are born in A-operand layout; dK, dV).
 //
 // Relative-position bias (videoswin.py:113-127,150-153): per token one code word; the bias of a
-// pair is table[code_q - code_k].  Keys are enumerated (w,d,h) so the 32 lanes of an MMA fragment
-// read 32 distinct table slots.  The -100 shift mask (videoswin.py:272-285) only exists in windows
+// pair is table[code_q - code_k]; with the natural (d,h,w) order on both sides the 32 lanes of an
+// MMA fragment read <= 14 consecutive slots (one shared-memory wavefront).  The -100 shift mask (videoswin.py:272-285) only exists in windows
 // on the wrapped border of a shifted block; those CTAs run a MASKED instantiation, the others
 // never test it.
 //
@@ -104,13 +104,13 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint3
 
 struct Smem {
   unsigned char *Qs, *Ks, *Vs, *dOs;
-  int *qrow, *krow;
-  uint32_t *qcode, *kcode, *qreg, *kreg;
+  int* qrow;                       // global token row of local index i (queries and keys alike)
+  uint32_t *qcode, *kcode, *qreg;
   float* tab;
 };
 
 // Per-token words: qcode = 4*(code + maxcode), kcode = 4*code (byte offsets; the pair's table slot is qcode - kcode),
-// qreg / kreg = shift-mask region id (compute_mask, videoswin.py:272-285).
+// qreg = shift-mask region id (compute_mask, videoswin.py:272-285).
 __device__ __forceinline__ bool win_build_tables(const WinParams& P, int p, int h, const Smem& S) {
   const WindowIndex& ix = P.win;
   const int nWw = ix.W / ix.ww, nWh = ix.H / ix.wh, nWd = ix.D / ix.wd;
@@ -121,41 +121,33 @@ __device__ __forceinline__ bool win_build_tables(const WinParams& P, int p, int 
   const int b = tq / nWd;
   const int od = id * ix.wd, oh = ih * ix.wh, ow = iw * ix.ww;
   const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
-  const int hw = ix.wh * ix.ww, dh = ix.wd * ix.wh;
-  const int inv_hw = small_inv(hw), inv_ww = small_inv(ix.ww), inv_wh = small_inv(ix.wh), inv_dh = small_inv(dh);
+  const int hw = ix.wh * ix.ww;
+  const int inv_hw = small_inv(hw), inv_ww = small_inv(ix.ww);
   // a window carries more than one mask region only where a shifted axis wraps: the last window along that axis
   const bool masked = (ix.sd > 0 && id == nWd - 1) || (ix.sh > 0 && ih == nWh - 1) || (ix.sw > 0 && iw == nWw - 1);
+  // Queries and keys share the natural (d,h,w) enumeration: the 8 queries x 4 keys of one MMA fragment register then
+  // touch at most 14 distinct, consecutive table slots (same address = broadcast), i.e. one wavefront per lookup.
   for (int i = threadIdx.x; i < P.NP; i += blockDim.x) {
     if (i < ix.N) {
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        int ld, lh, lw;
-        if (which == 0) {            // queries: natural (d,h,w) order
-          ld = small_div(i, inv_hw);
-          const int rem = i - ld * hw;
-          lh = small_div(rem, inv_ww);
-          lw = rem - lh * ix.ww;
-        } else {                     // keys: (w,d,h) order, h fastest
-          lw = small_div(i, inv_dh);
-          const int rem = i - lw * dh;
-          ld = small_div(rem, inv_wh);
-          lh = rem - ld * ix.wh;
-        }
-        const int cd = od + ld, ch = oh + lh, cw = ow + lw;
-        int d = cd + ix.sd; if (d >= ix.D) d -= ix.D;   // shifted[c] = x[(c + shift) mod size]  (videoswin.py:206)
-        int hh = ch + ix.sh; if (hh >= ix.H) hh -= ix.H;
-        int w = cw + ix.sw; if (w >= ix.W) w -= ix.W;
-        const int row = ((b * ix.D + d) * ix.H + hh) * ix.W + w;
-        uint32_t reg = 0;
-        if (masked) reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
-                                     ix.region(cw, ix.W, ix.ww, ix.sw));
-        const int code = ld * cH + lh * cW + lw;
-        if (which == 0) { S.qrow[i] = row; S.qcode[i] = (uint32_t)(4 * (code + P.maxcode)); S.qreg[i] = reg; }
-        else            { S.krow[i] = row; S.kcode[i] = (uint32_t)(4 * code); S.kreg[i] = reg; }
-      }
+      const int ld = small_div(i, inv_hw);
+      const int rem = i - ld * hw;
+      const int lh = small_div(rem, inv_ww);
+      const int lw = rem - lh * ix.ww;
+      const int cd = od + ld, ch = oh + lh, cw = ow + lw;
+      int d = cd + ix.sd; if (d >= ix.D) d -= ix.D;   // shifted[c] = x[(c + shift) mod size]  (videoswin.py:206)
+      int hh = ch + ix.sh; if (hh >= ix.H) hh -= ix.H;
+      int w = cw + ix.sw; if (w >= ix.W) w -= ix.W;
+      uint32_t reg = 0;
+      if (masked) reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 +
+                                   ix.region(cw, ix.W, ix.ww, ix.sw));
+      const int code = ld * cH + lh * cW + lw;
+      S.qrow[i] = ((b * ix.D + d) * ix.H + hh) * ix.W + w;
+      S.qcode[i] = (uint32_t)(4 * (code + P.maxcode));
+      S.kcode[i] = (uint32_t)(4 * code);
+      S.qreg[i] = reg;
     } else {
-      S.qrow[i] = -1; S.krow[i] = -1;
-      S.qcode[i] = (uint32_t)(4 * P.maxcode); S.kcode[i] = 0u; S.qreg[i] = 0u; S.kreg[i] = 0u;
+      S.qrow[i] = -1;
+      S.qcode[i] = (uint32_t)(4 * P.maxcode); S.kcode[i] = 0u; S.qreg[i] = 0u;
     }
   }
   const float* src = ix.table + (size_t)(P.center - P.maxcode) * ix.heads + h;
@@ -197,7 +189,7 @@ struct Lane {
 
 static inline size_t win_smem_bytes(int NP, int n_used, bool bwd, int n_dq_warps) {
   size_t b = (size_t)(bwd ? 4 : 3) * NP * ROWB;   // Q K V (dO)
-  b += (size_t)6 * NP * 4;                        // qrow krow qcode kcode qreg kreg
+  b += (size_t)4 * NP * 4;                        // qrow qcode kcode qreg
   const size_t tab = ((size_t)n_used * 4 + 15) / 16 * 16;
   b += tab;                                       // bias slice
   if (bwd) b += (size_t)2 * NP * 4 + (size_t)n_dq_warps * (tab + 16 * 40 * 4 + 16);   // {lse, -delta}, per-warp tables + staging + parking word
@@ -211,12 +203,10 @@ __device__ __forceinline__ Smem carve(unsigned char* smem, int NP, bool bwd) {
   S.Vs = S.Ks + NP * ROWB;
   S.dOs = S.Vs + NP * ROWB;
   S.qrow = (int*)(bwd ? S.dOs + NP * ROWB : S.dOs);
-  S.krow = S.qrow + NP;
-  S.qcode = (uint32_t*)(S.krow + NP);
+  S.qcode = (uint32_t*)(S.qrow + NP);
   S.kcode = S.qcode + NP;
   S.qreg = S.kcode + NP;
-  S.kreg = S.qreg + NP;
-  S.tab = (float*)(S.kreg + NP);
+  S.tab = (float*)(S.qreg + NP);
   return S;
 }
 
@@ -360,7 +350,7 @@ __device__ __forceinline__ void fwd_rows(const WinParams& P, const Smem& S, cons
   R.mref[0] = R.mref[1] = -INFINITY;
   R.kb0 = Ks + L.b_off[0]; R.kb1 = Ks + L.b_off[1];
   R.vt0 = Vs + L.bt_off[0]; R.vt1 = Vs + L.bt_off[1];
-  R.kc = sm_addr(S.kcode) + L.t4 * 8; R.kr = sm_addr(S.kreg) + L.t4 * 8;
+  R.kc = sm_addr(S.kcode) + L.t4 * 8; R.kr = sm_addr(S.qreg) + L.t4 * 8;
   const int nfull = N >> 6;
 #pragma unroll 1
   for (int kb = 0; kb < nfull; ++kb) fwd_block<MASKED, false>(L, R, 64, P.scale);
@@ -391,8 +381,8 @@ window_fwd_kernel(WinParams P) {
   const bool masked = win_build_tables(P, p, h, S);
   __syncthreads();
   win_load_rows(S.Qs, P.qkv, P.ld, col0, S.qrow, P.NP);
-  win_load_rows(S.Ks, P.qkv + C, P.ld, col0, S.krow, P.NP);
-  win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.krow, P.NP);
+  win_load_rows(S.Ks, P.qkv + C, P.ld, col0, S.qrow, P.NP);
+  win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.qrow, P.NP);
   cp_commit();
   cp_wait_all();
   __syncthreads();
@@ -531,7 +521,7 @@ __device__ __forceinline__ void bwd_dq_unit(const WinParams& P, const Smem& S, c
   for (int i = 0; i < 4; ++i) R.dq[i][0] = R.dq[i][1] = R.dq[i][2] = R.dq[i][3] = 0.f;
   R.kb0 = Ks + L.b_off[0]; R.kb1 = Ks + L.b_off[1]; R.vb0 = Vs + L.b_off[0]; R.vb1 = Vs + L.b_off[1];
   R.kt0 = Ks + L.bt_off[0]; R.kt1 = Ks + L.bt_off[1];
-  R.kc = sm_addr(S.kcode) + L.t4 * 8; R.kr = sm_addr(S.kreg) + L.t4 * 8;
+  R.kc = sm_addr(S.kcode) + L.t4 * 8; R.kr = sm_addr(S.qreg) + L.t4 * 8;
   R.kcl = sm_addr(S.kcode) + L.lane * 4;
   R.my_qcode = S.qcode[rb * 16 + (L.lane & 15)];
   R.gtab = gtab_s;
@@ -587,12 +577,14 @@ __device__ __forceinline__ void dkv_sweep(const Lane& L, DkvRow& R, int left, fl
   constexpr int LO = SUB * 256;
   const int npair = TAIL ? min(2, (left + 15) >> 4) : 2;
   float s[4][4], dp[4][4];   // rows = keys (g, g+8), cols = queries
+  float4 ln4[4];             // {lse, -delta} of this lane's two query columns, per n-tile
   static_for<2>([&](auto pr_) {
     constexpr int pr = decltype(pr_)::value;
     if (!TAIL || pr < npair) {
       uint32_t b[4];
-      const float4 l0 = ld_v4f32_o<LO + pr * 128>(R.ln);        // {lse, -delta} of the two query columns, n-tile 2*pr
-      const float4 l1 = ld_v4f32_o<LO + pr * 128 + 64>(R.ln);   // n-tile 2*pr + 1
+      ln4[pr * 2] = ld_v4f32_o<LO + pr * 128>(R.ln);
+      ln4[pr * 2 + 1] = ld_v4f32_o<LO + pr * 128 + 64>(R.ln);
+      const float4 l0 = ln4[pr * 2], l1 = ln4[pr * 2 + 1];
       ldsm4_o<QO + pr * 16 * ROWB>(b, R.qb0);
       mma_init(s[pr * 2], R.kf[0], b, 0.f, 0.f, 0.f, 0.f);
       mma_init(s[pr * 2 + 1], R.kf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
@@ -613,7 +605,7 @@ __device__ __forceinline__ void dkv_sweep(const Lane& L, DkvRow& R, int left, fl
     float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
     if (!TAIL || (nt >> 1) < npair) {
       const uint2 qc = ld_v2u32_o<CO + nt * 32>(R.qc);       // two consecutive queries (columns of S^T)
-      const float4 l4 = ld_v4f32_o<LO + nt * 64>(R.ln);      // lse = +inf on padding queries -> p = 0
+      const float4 l4 = ln4[nt];                             // lse = +inf on padding queries -> p = 0
       uint2 qr = make_uint2(0u, 0u);
       if (MASKED) qr = ld_v2u32_o<CO + nt * 32>(R.qr);
       const float nl[2] = {-l4.x * kLog2e, -l4.z * kLog2e};
@@ -665,7 +657,7 @@ __device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, 
   }
   const int j0 = jb * 16 + L.g;   // keys j0, j0+8 (padding keys: K/V rows are zero, results dropped)
   R.kaddr[0] = tab_s - S.kcode[j0]; R.kaddr[1] = tab_s - S.kcode[j0 + 8];
-  R.krg[0] = S.kreg[j0]; R.krg[1] = S.kreg[j0 + 8];
+  R.krg[0] = S.qreg[j0]; R.krg[1] = S.qreg[j0 + 8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -691,7 +683,7 @@ __device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, 
   for (int r = 0; r < 2; ++r) {
     const int j = j0 + r * 8;
     if (j < N) {
-      bf16* dstk = P.dqkv + (size_t)S.krow[j] * P.lddqkv + C + col0;
+      bf16* dstk = P.dqkv + (size_t)S.qrow[j] * P.lddqkv + C + col0;
       bf16* dstv = dstk + C;
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt) {
@@ -717,8 +709,8 @@ window_bwd_kernel(WinParams P) {
   const bool masked = win_build_tables(P, p, h, S);
   __syncthreads();
   win_load_rows(S.Qs, P.qkv, P.ld, col0, S.qrow, NP);
-  win_load_rows(S.Ks, P.qkv + C, P.ld, col0, S.krow, NP);
-  win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.krow, NP);
+  win_load_rows(S.Ks, P.qkv + C, P.ld, col0, S.qrow, NP);
+  win_load_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.qrow, NP);
   win_load_rows(S.dOs, P.dO, P.ldo, col0, S.qrow, NP);
   cp_commit();
   for (int i = threadIdx.x; i < NP; i += blockDim.x) ln_sm[2 * i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] : INFINITY;
@@ -819,7 +811,7 @@ bool window_cta_eligible(const WindowIndex& ix, int hd) {
   WinParams P = {};
   win_geometry(P, ix, 1);
   if (4 * (2 * P.maxcode + 1) >= 65536) return false;
-  if (ix.wh * ix.ww > 256 || ix.wd * ix.wh > 256) return false;   // small_div range
+  if (ix.wh * ix.ww > 256) return false;   // small_div range
   int q, k;
   return win_smem_bytes(P.NP, P.n_used, false, 0) <= kSmemLimit && bwd_warps(P.NP, P.n_used, q, k);
 }
