@@ -61,7 +61,7 @@ def main():
     for ev in prof.events():
         if ev.device_type is None or "cuda" not in str(ev.device_type).lower():
             continue
-        name = re.sub(r"\(.*", "", ev.name).replace("void ", "").replace("valor::", "")
+        name = re.sub(r"\(anonymous namespace\)::|unnamed>::", "", ev.name); name = re.sub(r"\(.*", "", name).replace("void ", "").replace("valor::", "")
         us = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
         a = agg[name]
         a[0] += 1

@@ -55,6 +55,10 @@ __device__ __forceinline__ void mma_init(float* d, const uint32_t* a, const uint
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
+// 8x8 b16 transpose across the warp: turns a non-transposed ldmatrix fragment into the transposed one
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+  uint32_t y; asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x)); return y;
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *(uint32_t*)&v;
@@ -424,16 +428,17 @@ __device__ __forceinline__ void dq_sweep(const Lane& L, DqRow& R, int left, floa
   constexpr int CO = SUB * 128;         // code-word offset
   const int npair = TAIL ? min(2, (left + 15) >> 4) : 2;
   float s[4][4], dp[4][4];
+  uint32_t kfr[2][2][4];   // K fragments of the sweep [pair][ks]: reused (transposed in registers) for dQ += dS.K
   static_for<2>([&](auto pr_) {
     constexpr int pr = decltype(pr_)::value;
     if (!TAIL || pr < npair) {
       uint32_t b[4];
-      ldsm4_o<KO + pr * 16 * ROWB>(b, R.kb0);
-      mma_init(s[pr * 2], R.qf[0], b, 0.f, 0.f, 0.f, 0.f);
-      mma_init(s[pr * 2 + 1], R.qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
-      ldsm4_o<KO + pr * 16 * ROWB>(b, R.kb1);
-      mma_acc(s[pr * 2], R.qf[1], b);
-      mma_acc(s[pr * 2 + 1], R.qf[1], b + 2);
+      ldsm4_o<KO + pr * 16 * ROWB>(kfr[pr][0], R.kb0);
+      mma_init(s[pr * 2], R.qf[0], kfr[pr][0], 0.f, 0.f, 0.f, 0.f);
+      mma_init(s[pr * 2 + 1], R.qf[0], kfr[pr][0] + 2, 0.f, 0.f, 0.f, 0.f);
+      ldsm4_o<KO + pr * 16 * ROWB>(kfr[pr][1], R.kb1);
+      mma_acc(s[pr * 2], R.qf[1], kfr[pr][1]);
+      mma_acc(s[pr * 2 + 1], R.qf[1], kfr[pr][1] + 2);
       ldsm4_o<KO + pr * 16 * ROWB>(b, R.vb0);   // dP - delta: the accumulator starts at -delta_i
       mma_init(dp[pr * 2], R.dof[0], b, R.ndel[0], R.ndel[0], R.ndel[1], R.ndel[1]);
       mma_init(dp[pr * 2 + 1], R.dof[0], b + 2, R.ndel[0], R.ndel[0], R.ndel[1], R.ndel[1]);
@@ -470,13 +475,15 @@ __device__ __forceinline__ void dq_sweep(const Lane& L, DqRow& R, int left, floa
   static_for<2>([&](auto kk_) {
     constexpr int kk = decltype(kk_)::value;
     if (!TAIL || kk < npair) {
-      uint32_t b[4];
-      ldsm4t_o<KO + kk * 16 * ROWB>(b, R.kt0);
-      mma_acc(R.dq[0], dsf[kk], b);
-      mma_acc(R.dq[1], dsf[kk], b + 2);
-      ldsm4t_o<KO + kk * 16 * ROWB>(b, R.kt1);
-      mma_acc(R.dq[2], dsf[kk], b);
-      mma_acc(R.dq[3], dsf[kk], b + 2);
+      // K as the B operand of dQ += dS.K is the 8x8-transposed image of the fragments fetched for S = Q.K^T:
+      // kfr[kk][ks] = {keys 0-7 | dims 16ks..+7, keys 0-7 | dims +8..+15, keys 8-15 | dims ..+7, keys 8-15 | dims +8..}
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t b0[2] = {movm_t(kfr[kk][ks][0]), movm_t(kfr[kk][ks][2])};
+        const uint32_t b1[2] = {movm_t(kfr[kk][ks][1]), movm_t(kfr[kk][ks][3])};
+        mma_acc(R.dq[ks * 2], dsf[kk], b0);
+        mma_acc(R.dq[ks * 2 + 1], dsf[kk], b1);
+      }
     }
   });
   if (want_dtab) {
