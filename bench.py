@@ -196,6 +196,10 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    # a rank that stops making progress (mismatched collective, dead peer) dumps its stacks and exits instead of
+    # holding the node until the launcher's own limit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("VALOR_BENCH_WATCHDOG_S", "420")), exit=True)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -261,7 +265,7 @@ def main():
     # ---- roofline pass: CUDA events around every GEMM launch of one more step (outside the timed region)
     roof = None
     peak_tf, peak_hbm, peak_kind = peaks()
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:   # every rank runs the probe step (it contains the step's collectives); rank 0 reports
         recs = []
         orig = K.gemm
 
