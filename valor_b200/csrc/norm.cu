@@ -34,11 +34,12 @@ template <> struct Vec4<bf16> {
 // ---------------------------------------------------------------------------------------
 // LayerNorm forward: y = (x - mean) * rstd * gamma + beta ; saves mean, rstd (fp32)
 // ---------------------------------------------------------------------------------------
+// generic N (N % 4 == 0): one warp per row, three passes over the (L1-resident) row
 template <typename T>
 __global__ void __launch_bounds__(256)
-layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int N,
-                     float eps) {
+layernorm_fwd_generic_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int N,
+                             float eps) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -74,12 +75,78 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
+// N == VPL*128: the row lives in registers (one read of x), and a warp works on R rows at once so that R*VPL
+// independent loads are in flight per lane -- a single 256-byte row per warp leaves HBM latency-bound.
+template <typename T, int VPL, int R>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, float eps) {
+  constexpr int N = VPL * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= M) return;
+  float f[R][VPL][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < M ? row0 + r : M - 1;   // clamp: tail rows are recomputed, never stored
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      Vec4<T> v; v.load(x + row * N + (k * 32 + lane) * 4);
+      v.get(f[r][k]);
+    }
+  }
+  float mean[R], rstd[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) s += f[r][k][0] + f[r][k][1] + f[r][k][2] + f[r][k][3];
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) mean[r] = warp_sum(mean[r]) / N;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float d = f[r][k][e] - mean[r]; ss += d * d; }
+    rstd[r] = ss;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(warp_sum(rstd[r]) / N + eps);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    const float4 g = *(const float4*)(gamma + c);
+    const float4 b = *(const float4*)(beta + c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r < M) {
+        float o[4];
+        o[0] = (f[r][k][0] - mean[r]) * rstd[r] * g.x + b.x;
+        o[1] = (f[r][k][1] - mean[r]) * rstd[r] * g.y + b.y;
+        o[2] = (f[r][k][2] - mean[r]) * rstd[r] * g.z + b.z;
+        o[3] = (f[r][k][3] - mean[r]) * rstd[r] * g.w + b.w;
+        Vec4<T> v; v.set(o); v.store(y + (row0 + r) * N + c);
+      }
+    }
+  }
+  if (lane < R && row0 + lane < M) {
+    float mo = mean[0], ro = rstd[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) if (lane == r) { mo = mean[r]; ro = rstd[r]; }
+    mean_out[row0 + lane] = mo; rstd_out[row0 + lane] = ro;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // LayerNorm backward: dx per row; dgamma/dbeta accumulated per lane in registers over the
 // rows a warp visits (each lane owns the same columns on every row), then reduced through
 // shared memory and flushed with one atomicAdd per column per CTA into fp32 gradients.
 // ---------------------------------------------------------------------------------------
-template <typename T, int VPL /* float4-groups per lane; N == VPL*128 */>
+template <typename T, int VPL /* float4-groups per lane; N == VPL*128 */, int R /* rows in flight per warp */>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ dres,
@@ -88,49 +155,76 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  float ag[VPL][4], ab[VPL][4];
+  constexpr bool kCacheGamma = VPL <= 4;   // wide rows re-read gamma from L1 instead of pinning 4*VPL registers
+  float ag[VPL][4], ab[VPL][4], gm[kCacheGamma ? VPL : 1][4];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k)
+  for (int k = 0; k < VPL; ++k) {
+    if (kCacheGamma) {
+      const float4 g = *(const float4*)(gamma + (k * 32 + lane) * 4);
+      gm[k][0] = g.x; gm[k][1] = g.y; gm[k][2] = g.z; gm[k][3] = g.w;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
-  for (long long row = (long long)blockIdx.x * nwarp + warp; row < M; row += (long long)gridDim.x * nwarp) {
-    const T* dyr = dy + row * N;
-    const T* xr = x + row * N;
-    const float mu = mean[row], rs = rstd[row];
-    float fdy[VPL][4], fxh[VPL][4];
-    float s1 = 0.f, s2 = 0.f;
+  }
+  for (long long row0 = ((long long)blockIdx.x * nwarp + warp) * R; row0 < M; row0 += (long long)gridDim.x * nwarp * R) {
+    float fdy[R][VPL][4], fxh[R][VPL][4], mu[R], rs[R], s1[R], s2[R];
+    Vec4<T> rv[R][VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int c = (k * 32 + lane) * 4;
-      Vec4<T> a, b; a.load(dyr + c); b.load(xr + c);
-      a.get(fdy[k]); b.get(fxh[k]);
-      const float4 g = *(const float4*)(gamma + c);
-      const float gg[4] = {g.x, g.y, g.z, g.w};
+    for (int r = 0; r < R; ++r) {   // all loads of the R rows are issued before the first use
+      const bool ok = row0 + r < M;
+      const long long row = ok ? row0 + r : M - 1;
+      mu[r] = mean[row]; rs[r] = rstd[row];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        fxh[k][e] = (fxh[k][e] - mu) * rs;
-        ag[k][e] += fdy[k][e] * fxh[k][e];
-        ab[k][e] += fdy[k][e];
-        fdy[k][e] *= gg[e];  // dy * gamma
-        s1 += fdy[k][e];
-        s2 += fdy[k][e] * fxh[k][e];
+      for (int k = 0; k < VPL; ++k) {
+        const int c = (k * 32 + lane) * 4;
+        Vec4<T> a, b; a.load(dy + row * N + c); b.load(x + row * N + c);
+        a.get(fdy[r][k]); b.get(fxh[r][k]);
+        if (dres != nullptr) rv[r][k].load(dres + row * N + c);
+        if (!ok) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) fdy[r][k][e] = 0.f;   // tail rows contribute nothing
+        }
       }
     }
-    s1 = warp_sum(s1) / N;
-    s2 = warp_sum(s2) / N;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int c = (k * 32 + lane) * 4;
-      float o[4];
+    for (int r = 0; r < R; ++r) {
+      float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = (fdy[k][e] - s1 - fxh[k][e] * s2) * rs;
-      if (dres != nullptr) {  // gradient arriving through the residual branch that bypasses this LN
-        Vec4<T> rv; rv.load(dres + row * N + c);
-        float rf[4]; rv.get(rf);
+      for (int k = 0; k < VPL; ++k) {
+        float gk[4];
+        if (kCacheGamma) { gk[0] = gm[k][0]; gk[1] = gm[k][1]; gk[2] = gm[k][2]; gk[3] = gm[k][3]; }
+        else { const float4 g = *(const float4*)(gamma + (k * 32 + lane) * 4); gk[0] = g.x; gk[1] = g.y; gk[2] = g.z; gk[3] = g.w; }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] += rf[e];
+        for (int e = 0; e < 4; ++e) {
+          fxh[r][k][e] = (fxh[r][k][e] - mu[r]) * rs[r];
+          ag[k][e] += fdy[r][k][e] * fxh[r][k][e];
+          ab[k][e] += fdy[r][k][e];
+          fdy[r][k][e] *= gk[e];  // dy * gamma
+          a1 += fdy[r][k][e];
+          a2 += fdy[r][k][e] * fxh[r][k][e];
+        }
       }
-      Vec4<T> v; v.set(o); v.store(dx + row * N + c);
+      s1[r] = a1; s2[r] = a2;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { s1[r] = warp_sum(s1[r]) / N; s2[r] = warp_sum(s2[r]) / N; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r < M) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int c = (k * 32 + lane) * 4;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = (fdy[r][k][e] - s1[r] - fxh[r][k][e] * s2[r]) * rs[r];
+          if (dres != nullptr) {  // gradient arriving through the residual branch that bypasses this LN
+            float rf[4]; rv[r][k].get(rf);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] += rf[e];
+          }
+          Vec4<T> v; v.set(o); v.store(dx + (row0 + r) * N + c);
+        }
+      }
     }
   }
 #pragma unroll
@@ -192,16 +286,16 @@ template <typename T>
 static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                            const void* dres, void* dx, float* dgamma, float* dbeta, long long M, int N, cudaStream_t st) {
   long long want = (M + 7) / 8;
-  int grid = (int)(want < (long long)num_sms() * 4 ? want : (long long)num_sms() * 4);
+  int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * N * sizeof(float);
-#define LN_BWD_CASE(V)                                                                                          \
+#define LN_BWD_CASE(V, RR)                                                                                      \
   case V * 128:                                                                                                 \
-    layernorm_bwd_kernel<T, V><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,           \
-                                                         (const T*)dres, (T*)dx, dgamma, dbeta, M, N);          \
+    layernorm_bwd_kernel<T, V, RR><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,       \
+                                                             (const T*)dres, (T*)dx, dgamma, dbeta, M, N);      \
     break;
   switch (N) {
-    LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(4) LN_BWD_CASE(6) LN_BWD_CASE(8) LN_BWD_CASE(16)
+    LN_BWD_CASE(1, 4) LN_BWD_CASE(2, 2) LN_BWD_CASE(4, 1) LN_BWD_CASE(6, 1) LN_BWD_CASE(8, 1) LN_BWD_CASE(16, 1)
     default:
       layernorm_bwd_generic_kernel<T><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,
                                                                 (const T*)dres, (T*)dx, dgamma, dbeta, M, N);
@@ -213,13 +307,26 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
 int layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                   long long M, int N, float eps, cudaStream_t st) {
   VALOR_REQUIRE(N % 4 == 0, "layernorm: N=%d must be a multiple of 4", N);
+  if (M == 0) return 0;
+#define LN_FWD_CASE(TT, V, RR)                                                                                   \
+  case V * 128: {                                                                                                \
+    const long long blocks = (M + 8 * RR - 1) / (8 * RR);                                                        \
+    VALOR_REQUIRE(blocks < 2147483647LL, "layernorm: too many rows");                                            \
+    layernorm_fwd_kernel<TT, V, RR><<<(unsigned)blocks, 256, 0, st>>>((const TT*)x, gamma, beta, (TT*)y, mean, rstd, M, eps); \
+    return check_launch("layernorm_fwd_kernel");                                                                 \
+  }
+  if (dtype == VALOR_DT_F32) {
+    switch (N) { LN_FWD_CASE(float, 1, 4) LN_FWD_CASE(float, 2, 2) LN_FWD_CASE(float, 4, 2) LN_FWD_CASE(float, 6, 1) LN_FWD_CASE(float, 8, 1) default: break; }
+  } else {
+    switch (N) { LN_FWD_CASE(bf16, 1, 4) LN_FWD_CASE(bf16, 2, 2) LN_FWD_CASE(bf16, 4, 2) LN_FWD_CASE(bf16, 6, 1) LN_FWD_CASE(bf16, 8, 1) default: break; }
+  }
+#undef LN_FWD_CASE
   const long long blocks = (M + 7) / 8;
   VALOR_REQUIRE(blocks < 2147483647LL, "layernorm: too many rows");
-  if (M == 0) return 0;
   if (dtype == VALOR_DT_F32)
-    layernorm_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, N, eps);
+    layernorm_fwd_generic_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, M, N, eps);
   else
-    layernorm_fwd_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, N, eps);
+    layernorm_fwd_generic_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, M, N, eps);
   return check_launch("layernorm_fwd_kernel");
 }
 
