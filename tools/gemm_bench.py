@@ -21,6 +21,10 @@ SHAPES = [  # (name, M, N, K, form)
     ("swin3.fc1.dgrad", 50176, 512, 2048, "nn"), ("swin1.fc1.dgrad", 802816, 128, 512, "nn"),
     ("swin3.fc1.wgrad", 2048, 512, 50176, "tn"), ("swin1.qkv.wgrad", 384, 128, 802816, "tn"),
     ("bert.fc1.wgrad", 3072, 768, 3072, "tn"), ("big", 8192, 8192, 8192, "nt"),
+    # fused epilogues: fc1 forward (bias + erf-GELU, pre-activation kept), fc2 dgrad (* GELU'(pre)), proj/fc2 (+ residual)
+    ("epi.swin1.fc1.gelu_pre", 802816, 512, 128, "nt"), ("epi.swin3.fc1.gelu_pre", 50176, 2048, 512, "nt"),
+    ("epi.swin1.fc2.dgrad.gelu_aux", 802816, 512, 128, "nn"), ("epi.swin3.fc2.dgrad.gelu_aux", 50176, 2048, 512, "nn"),
+    ("epi.swin1.fc2.res", 802816, 128, 512, "nt"), ("epi.swin3.fc2.res", 50176, 512, 2048, "nt"),
 ]
 
 
@@ -51,7 +55,14 @@ def main():
         b = torch.randn((N, Kd) if b_k else (Kd, N), device="cuda", dtype=torch.bfloat16)
         acc = form == "tn"
         out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if acc else torch.bfloat16)
-        ms = bench(lambda: K.gemm(a, b, a_kmajor=a_k, b_kmajor=b_k, out=out, accumulate=acc))
+        kw = {}
+        if "gelu_pre" in name:
+            kw = dict(bias=torch.randn(N, device="cuda"), act=K.ACT_GELU, want_preact=True)
+        elif "gelu_aux" in name:
+            kw = dict(act=K.ACT_GELU, act_aux=torch.randn(M, N, device="cuda", dtype=torch.bfloat16))
+        elif name.endswith(".res"):
+            kw = dict(bias=torch.randn(N, device="cuda"), residual=torch.randn(M, N, device="cuda", dtype=torch.bfloat16))
+        ms = bench(lambda: K.gemm(a, b, a_kmajor=a_k, b_kmajor=b_k, out=out, accumulate=acc, **kw))
         A = a if a_k else a.t()
         Bt = b.t() if b_k else b
         ms_cublas = bench(lambda: torch.matmul(A, Bt))
