@@ -230,6 +230,9 @@ def test_mha(dtype, case):
     ((1, 8, 14, 7), (8, 7, 7), (0, 3, 0), 2),
     ((1, 16, 7, 7), (8, 7, 7), (4, 0, 0), 2),
     ((3, 4, 7, 7), (4, 7, 7), (0, 0, 0), 8),
+    ((1, 16, 7, 7), (8, 7, 7), (4, 0, 0), 4),     # temporal shift: mask regions along d, one-CTA-per-window kernels
+    ((2, 4, 14, 14), (4, 7, 7), (0, 3, 3), 4),    # 196-token windows, masked border windows
+    ((1, 8, 21, 14), (8, 7, 7), (0, 3, 3), 1),    # 392-token windows, 3x2 window grid, single head
 ])
 def test_window_attention(dtype, grid, win, shift, heads):
     """shift / partition / relative-position bias / -100 mask evaluated in-kernel vs the reference's
