@@ -93,13 +93,13 @@ int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm,
 int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
                   void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid, const unsigned char* causal,
-                  float scale, int backend, void* stream);
+                  const int* q_key_range, float scale, int backend, void* stream);
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                   long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta,
                   void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp,
                   void* dV_lp, long long lddkv_lp, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid,
-                  const unsigned char* causal, float scale, int backend, void* stream);
+                  const unsigned char* causal, const int* q_key_range, float scale, int backend, void* stream);
 
 /* ---- VideoSwin shifted-window attention: WindowAttention3D.forward (videoswin.py:137-163)
  * together with torch.roll / window_partition / window_reverse / compute_mask

@@ -113,13 +113,23 @@ def _mha_mask(p, Nq, nk, max_nk, key_valid, causal):
     return add
 
 
+def _range_mask(add, q_key_range, nk):
+    """-inf outside each query's visible key range [lo, hi) (keys that do not exist for that query)."""
+    if q_key_range is None:
+        return add
+    j = torch.arange(nk)[None, :]
+    r = q_key_range.cpu().long()
+    out = (j < r[:, 0:1]) | (j >= r[:, 1:2])
+    return (add + torch.zeros(r.shape[0], nk)).masked_fill(out, float("-inf"))
+
+
 def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None, key_valid=None,
-            causal=None, backend=0):
+            causal=None, q_key_range=None, backend=0):
     o = torch.zeros(q.shape[0], H * hd, dtype=q.dtype)
     lse = torch.zeros(P_, H, Nq)
     for p in range(P_):
         q0, k0, nk = _mha_problem(p, Nq, max_nk, q_row0, kv_row0, kv_len)
-        add = _mha_mask(p, Nq, nk, max_nk, key_valid, causal)
+        add = _range_mask(_mha_mask(p, Nq, nk, max_nk, key_valid, causal), q_key_range, nk)
         for h in range(H):
             qq = q[q0:q0 + Nq, h * hd:(h + 1) * hd].float()
             kk = k[k0:k0 + nk, h * hd:(h + 1) * hd].float()
@@ -131,11 +141,11 @@ def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv
 
 
 def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
-            key_valid=None, causal=None, dkv_out=None, backend=0):
+            key_valid=None, causal=None, dkv_out=None, q_key_range=None, backend=0):
     dkv = torch.zeros(k.shape[0], 2 * H * hd)
     for p in range(P_):
         q0, k0, nk = _mha_problem(p, Nq, max_nk, q_row0, kv_row0, kv_len)
-        add = _mha_mask(p, Nq, nk, max_nk, key_valid, causal)
+        add = _range_mask(_mha_mask(p, Nq, nk, max_nk, key_valid, causal), q_key_range, nk)
         for h in range(H):
             sl = slice(h * hd, (h + 1) * hd)
             qq, kk, vv = q[q0:q0 + Nq, sl].float(), k[k0:k0 + nk, sl].float(), v[k0:k0 + nk, sl].float()

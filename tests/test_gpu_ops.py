@@ -170,7 +170,7 @@ def test_l2norm(dtype):
 # attention
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("case", ["bert_self", "ast", "cross"])
+@pytest.mark.parametrize("case", ["bert_self", "ast", "cross", "cross_merged"])
 def test_mha(dtype, case):
     k = K()
     H, hd = 12, 64
@@ -188,6 +188,17 @@ def test_mha(dtype, case):
         qkv = rnd(P_ * Nq, 3 * Hd, dtype=dtype, seed=1)
         q, kk, v = qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:]
         kw = {}
+    elif case == "cross_merged":
+        # the three caption passes of a sample as ONE problem: 3*32 queries over the sample's 650 media tokens, every
+        # query restricted to its pass's key subset (tva: all, tv: video rows, ta: audio rows)
+        B, S, T = 2, 650, 32
+        P_, Nq, nk = B, 3 * T, S
+        q = rnd(P_ * Nq, Hd, dtype=dtype, seed=1)
+        kvb = rnd(B * S, 2 * Hd, dtype=dtype, seed=2)
+        kk, v = kvb[:, :Hd], kvb[:, Hd:]
+        ranges = [(0, 650), (0, 392), (392, 258)]
+        kw = dict(q_key_range=torch.tensor([[ranges[i // T][0], ranges[i // T][0] + ranges[i // T][1]] for i in range(Nq)],
+                                           dtype=torch.int32))
     else:
         B, S, Nq = 2, 100, 32
         P_ = 3 * B
@@ -204,7 +215,7 @@ def test_mha(dtype, case):
     dq_r = torch.zeros(P_ * Nq, Hd)
     dkv_r = R.mha_bwd(q, kk, v, o_r, do, lse_r, dq_r, P_, H, hd, Nq, nk, scale, **kw)
     kwd = {a: dev(b) for a, b in kw.items()}
-    if case == "cross":
+    if case in ("cross", "cross_merged"):
         qd, kvd = dev(q, dtype), dev(kvb, dtype)
         kd, vd = kvd[:, :Hd], kvd[:, Hd:]
     else:
@@ -217,8 +228,8 @@ def test_mha(dtype, case):
     dkv = k.mha_bwd(qd, kd, vd, o, dev(do, dtype), lse, dq, P_, H, hd, Nq, nk, scale, **kwd)
     close(dq, dq_r, dtype, "mha dq")
     close(dkv, dkv_r, dtype, "mha dkv")
-    if case != "cross":  # self-attention: every K/V row has one owner -> direct outputs in the compute dtype
-        dkv2 = torch.full((P_ * Nq, 2 * Hd), 7.0, device="cuda", dtype=dtype)
+    if case != "cross":  # every K/V row has one owner -> direct outputs in the compute dtype
+        dkv2 = torch.full((kd.shape[0], 2 * Hd), 7.0, device="cuda", dtype=dtype)
         k.mha_bwd(qd, kd, vd, o, dev(do, dtype), lse, dq, P_, H, hd, Nq, nk, scale, dkv_out=(dkv2[:, :Hd], dkv2[:, Hd:]), **kwd)
         close(dkv2, dkv_r, dtype, "mha dkv direct")
 

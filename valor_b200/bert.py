@@ -176,7 +176,9 @@ class BertModel(nn.Module):
     # ------------------------------------------------------------------------------
     def encode(self, tokens, casual, media=None, media_ranges=None, n_media_samples=None):
         """Batched encoder pass.
-        tokens [R, T] int64 (R = n_pass * B sequences, pass-major); casual: list[bool] per pass or bool;
+        tokens [R, T] int64, R = B * n_pass sequences in SAMPLE-major order (row r = b * n_pass + pass): the text rows
+        of one sample's passes are adjacent, so its cross-attention is one problem of n_pass*T queries over the
+        sample's media tokens; casual: list[bool] per pass or bool;
         media [B*S, H] per-sample media tokens and media_ranges = [(start, len)] per pass, or None.
         Returns hidden states [R*T, H]."""
         R, T = tokens.shape
@@ -198,22 +200,26 @@ class BertModel(nn.Module):
         ck = (R, T, tuple(cas), tuple(media_ranges) if media_ranges else None, n_media_samples,
               media.shape[0] if media is not None else 0, str(dev))
         if ck not in cache:
-            c_t = torch.tensor([1 if c else 0 for c in cas for _ in range(Bp)], dtype=torch.uint8, device=dev)
-            r_t = l_t = None
+            c_t = torch.tensor([1 if cas[r % n_pass] else 0 for r in range(R)], dtype=torch.uint8, device=dev)
+            r_t = l_t = q_t = None
+            u0 = ulen = 0
             if media is not None:
+                assert n_media_samples == Bp, "one media block per sample"
                 S_ = media.shape[0] // n_media_samples
-                r_t = torch.tensor([b * S_ + st for (st, ln) in media_ranges for b in range(n_media_samples)],
-                                   dtype=torch.int32, device=dev)
-                l_t = torch.tensor([ln for (st, ln) in media_ranges for b in range(n_media_samples)],
-                                   dtype=torch.int32, device=dev)
-            cache[ck] = (c_t, r_t, l_t)
-        causal, row0_c, lens_c = cache[ck]
+                u0 = min(st for st, ln in media_ranges)                      # union of the passes' key ranges
+                ulen = max(st + ln for st, ln in media_ranges) - u0
+                r_t = torch.tensor([b * S_ + u0 for b in range(Bp)], dtype=torch.int32, device=dev)
+                l_t = torch.full((Bp,), ulen, dtype=torch.int32, device=dev)
+                if n_pass > 1 or (u0, ulen) != tuple(media_ranges[0]):
+                    q_t = torch.tensor([[media_ranges[i // T][0] - u0, media_ranges[i // T][0] - u0 + media_ranges[i // T][1]]
+                                        for i in range(n_pass * T)], dtype=torch.int32, device=dev)
+            cache[ck] = (c_t, r_t, l_t, q_t, ulen, media is not None and u0 == 0 and ulen == media.shape[0] // n_media_samples)
+        causal, row0_c, lens_c, qrange_c, ulen, kv_full = cache[ck]
         self_spec = dict(P=R, H=H, hd=hd, Nq=T, max_nk=T, scale=1.0 / math.sqrt(hd), key_valid=key_valid, causal=causal)
         cross_spec = None
         if media is not None:
-            row0, lens = row0_c, lens_c
-            cross_spec = dict(P=R, H=H, hd=hd, Nq=T, max_nk=max(ln for _, ln in media_ranges),
-                              scale=1.0 / math.sqrt(hd), kv_row0=row0, kv_len=lens)
+            cross_spec = dict(P=Bp, H=H, hd=hd, Nq=n_pass * T, max_nk=ulen, scale=1.0 / math.sqrt(hd), kv_row0=row0_c,
+                              kv_len=lens_c, q_key_range=qrange_c, kv_exclusive=True, kv_full=kv_full)
         for layer in self.encoder.layer:
             h = layer.run(h, self_spec, media, cross_spec)
         return h

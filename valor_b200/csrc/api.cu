@@ -148,9 +148,11 @@ static MhaIndex make_mha(int Nq, int max_nk, const int* q_row0, const int* kv_ro
 int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
                   void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid, const unsigned char* causal,
-                  float scale, int backend, void* stream) {
+                  const int* q_key_range, float scale, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
+  ix.q_key_range = q_key_range;
+  VALOR_REQUIRE(q_key_range == nullptr || max_nk < 65535, "valor_mha_fwd: per-query key ranges need max_nk < 65535");
   const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O);
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_fwd: tensor backend requested but not eligible");
   if (backend != VALOR_BACKEND_SIMT && ok) return mha_mma_fwd(ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, ST);
@@ -161,9 +163,11 @@ int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const 
                   void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp,
                   void* dV_lp, long long lddkv_lp, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid,
-                  const unsigned char* causal, float scale, int backend, void* stream) {
+                  const unsigned char* causal, const int* q_key_range, float scale, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
+  ix.q_key_range = q_key_range;
+  VALOR_REQUIRE(q_key_range == nullptr || max_nk < 65535, "valor_mha_bwd: per-query key ranges need max_nk < 65535");
   const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O) && (lddq % 8 == 0) &&
                   (((uintptr_t)dQ | (uintptr_t)dO) & 15) == 0 && delta != nullptr;
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_bwd: tensor backend requested but not eligible");

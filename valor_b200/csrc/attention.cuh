@@ -15,6 +15,9 @@ struct MhaIndex {
   const int* kv_len;   // [P] key count, or null -> max_nk
   const unsigned char* key_valid;  // [P, max_nk] 1 = real token, or null
   const unsigned char* causal;     // [P] 1 = lower-triangular, or null
+  const int* q_key_range = nullptr;  // [Nq][2] query i only sees keys lo <= j < hi of its problem (others do not exist
+                                     // for it: -inf, not -10000), or null.  Lets the three caption passes of one
+                                     // sample -- same media tokens, different key subsets -- run as ONE problem.
 
   __device__ __forceinline__ int nk(int p) const { return kv_len ? kv_len[p] : max_nk; }
   __device__ __forceinline__ size_t qrow(int p, int i) const { return (size_t)(q_row0 ? q_row0[p] : p * Nq) + i; }
@@ -22,6 +25,7 @@ struct MhaIndex {
   __device__ __forceinline__ float qscale(float) const { return 1.f; }
   __device__ __forceinline__ float sscale(float s) const { return s; }
   __device__ __forceinline__ float add(int p, int, int i, int j) const {
+    if (q_key_range && (j < q_key_range[2 * i] || j >= q_key_range[2 * i + 1])) return -INFINITY;
     bool ok = true;
     if (key_valid) ok = key_valid[(size_t)p * max_nk + j] != 0;
     if (causal && causal[p] && j > i) ok = false;

@@ -22,7 +22,7 @@ static constexpr int BQ = 64, BKEY = 64;
 // ---- per-problem tables in shared memory -------------------------------------------------
 // One 32-bit info word per token keeps the per-element work short:
 //   window : bits[0,16) relative-position code (query words carry code + center), bits[16,24) mask region
-//   mha    : bit0 = key is padding (-10000)
+//   mha    : key words: bit0 = key is padding (-10000); query words: visible key range lo | hi << 16
 //   both   : bit31 = key beyond the problem's key count (-inf, only the ragged last block)
 struct Tables {
   int* qrow;            // [NqPad] global row of query i (-1 = padding)
@@ -31,7 +31,7 @@ struct Tables {
   uint32_t* kinfo;      // [NkPad]
   float* tab2;          // window: this head's column of the bias table, pre-multiplied by log2(e)
   uint32_t qrow_s, krow_s, qinfo_s, kinfo_s, tab2_s;  // the same arrays as 32-bit shared addresses
-  int causal, nq, nk, shifted;
+  int causal, nq, nk, shifted, ranged;
 };
 
 
@@ -45,6 +45,7 @@ __device__ __forceinline__ float score2(const Tables& t, float s, float sc2, uin
   } else {
     v = s * sc2;
     if ((kj & 1u) || (t.causal && j > i)) v += M10000_2;
+    if (t.ranged && ((uint32_t)j < (qi & 0xffffu) || (uint32_t)j >= (qi >> 16))) v = -INFINITY;   // key outside this query's range
   }
   return v;
 }
@@ -78,6 +79,7 @@ __device__ __forceinline__ void build_tables(Tables& t, unsigned char* base, con
     const WindowIndex& ix = P.win;
     t.nq = t.nk = ix.N;
     t.causal = 0;
+    t.ranged = 0;
     t.shifted = (ix.sd | ix.sh | ix.sw) != 0;
     const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
     const int center = (ix.WD - 1) * cH + (ix.WH - 1) * cW + (ix.WW - 1);
@@ -122,7 +124,13 @@ __device__ __forceinline__ void build_tables(Tables& t, unsigned char* base, con
     t.nq = ix.Nq;
     t.nk = ix.nk(p);
     t.causal = ix.causal ? (int)ix.causal[p] : 0;
-    for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) { t.qrow[i] = i < t.nq ? (int)ix.qrow(p, i) : -1; t.qinfo[i] = 0; }
+    t.ranged = ix.q_key_range != nullptr;
+    for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) {   // qinfo: visible key range lo | hi << 16
+      t.qrow[i] = i < t.nq ? (int)ix.qrow(p, i) : -1;
+      uint32_t w = 0xffff0000u;
+      if (ix.q_key_range != nullptr && i < t.nq) w = (uint32_t)ix.q_key_range[2 * i] | ((uint32_t)ix.q_key_range[2 * i + 1] << 16);
+      t.qinfo[i] = w;
+    }
     for (int j = threadIdx.x; j < nk_pad; j += blockDim.x) {
       t.krow[j] = j < t.nk ? (int)ix.krow(p, j) : -1;
       uint32_t w = 0;
@@ -163,6 +171,28 @@ __device__ __forceinline__ void load_tile_async(unsigned char* dst, const bf16* 
   }
 }
 
+// Key blocks a 64-query block has to visit: the union of its queries' visible key ranges (every warp computes the same
+// pair from the query words, no barrier).  Without per-query ranges this is [0, ceil(nk/64)).
+__device__ __forceinline__ void key_block_span(const Tables& t, int q0, int& kb0, int& kb1) {
+  const int nkb = (t.nk + BKEY - 1) / BKEY;
+  kb0 = 0; kb1 = nkb;
+  if (!t.ranged) return;
+  const int lane = threadIdx.x & 31;
+  uint32_t lo = 0xffffu, hi = 0u;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = q0 + lane + 32 * r;
+    if (i < t.nq) { const uint32_t w = t.qinfo[i]; lo = min(lo, w & 0xffffu); hi = max(hi, w >> 16); }
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, sft));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, sft));
+  }
+  kb0 = min((int)lo / BKEY, nkb);
+  kb1 = max(kb0, min(((int)hi + BKEY - 1) / BKEY, nkb));
+}
+
 // ==========================================================================================
 // forward: grid (ceil(Nq/64), P, H), 128 threads; warp w owns query rows [w*16, w*16+16)
 // ==========================================================================================
@@ -179,9 +209,11 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
   build_tables<WINDOW>(t, KVs + 4 * TILE, P, p, h, nq_pad, nk_pad);
   __syncthreads();
   const int col0 = h * HD;
+  int kb0, kb1;
+  key_block_span(t, qb * BQ, kb0, kb1);
   load_tile_async<HD>(Qs, P.Q, P.ldq, col0, t.qrow_s, qb * BQ);
-  load_tile_async<HD>(KVs, P.K, P.ldk, col0, t.krow_s, 0);
-  load_tile_async<HD>(KVs + TILE, P.V, P.ldv, col0, t.krow_s, 0);
+  load_tile_async<HD>(KVs, P.K, P.ldk, col0, t.krow_s, kb0 * BKEY);
+  load_tile_async<HD>(KVs + TILE, P.V, P.ldv, col0, t.krow_s, kb0 * BKEY);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -199,16 +231,15 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
   const int i0 = qb * BQ + warp * 16 + g;  // rows i0 and i0+8
   const float sc2 = P.scale * LOG2E;
   const uint32_t qinf[2] = {t.qinfo[i0], t.qinfo[i0 + 8]};
-  const int nkb = (t.nk + BKEY - 1) / BKEY;
-  for (int kb = 0; kb < nkb; ++kb) {
-    unsigned char* Ks = KVs + (kb & 1) * 2 * TILE;
+  for (int kb = kb0; kb < kb1; ++kb) {
+    unsigned char* Ks = KVs + ((kb - kb0) & 1) * 2 * TILE;
     unsigned char* Vs = Ks + TILE;
-    if (kb > 0) {  // block kb was prefetched during block kb-1
+    if (kb > kb0) {  // block kb was prefetched during block kb-1
       cp_async_wait<0>();
       __syncthreads();
     }
-    if (kb + 1 < nkb) {  // prefetch the next K/V block into the other buffer (its readers finished at the barrier above)
-      unsigned char* Kn = KVs + ((kb + 1) & 1) * 2 * TILE;
+    if (kb + 1 < kb1) {  // prefetch the next K/V block into the other buffer (its readers finished at the barrier above)
+      unsigned char* Kn = KVs + ((kb + 1 - kb0) & 1) * 2 * TILE;
       load_tile_async<HD>(Kn, P.K, P.ldk, col0, t.krow_s, (kb + 1) * BKEY);
       load_tile_async<HD>(Kn + TILE, P.V, P.ldv, col0, t.krow_s, (kb + 1) * BKEY);
       cp_async_commit();
@@ -340,8 +371,10 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   load_tile_async<HD>(Qs, P.Q, P.ldq, col0, t.qrow_s, qb * BQ);
   load_tile_async<HD>(dOs, P.dO, P.ldo, col0, t.qrow_s, qb * BQ);
   load_tile_async<HD>(KVs + 2 * TILE, P.O, P.ldo, col0, t.qrow_s, qb * BQ);  // O tile (buffer 1), only for delta
-  load_tile_async<HD>(KVs, P.K, P.ldk, col0, t.krow_s, 0);                   // first K/V block (buffer 0)
-  load_tile_async<HD>(KVs + TILE, P.V, P.ldv, col0, t.krow_s, 0);
+  int kb0, kb1;
+  key_block_span(t, qb * BQ, kb0, kb1);
+  load_tile_async<HD>(KVs, P.K, P.ldk, col0, t.krow_s, kb0 * BKEY);          // first K/V block (buffer 0)
+  load_tile_async<HD>(KVs + TILE, P.V, P.ldv, col0, t.krow_s, kb0 * BKEY);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -376,21 +409,20 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   const float sc = P.scale, sc2 = P.scale * LOG2E;
   const int il = warp * 16 + g;
   const int i0 = qb * BQ + il;
-  const int nkb = (t.nk + BKEY - 1) / BKEY;
   __syncthreads();  // lse_s / del_s visible
   // padding query rows (i >= nq) get lse = +inf -> p = 0 -> no gradient, no bias-table contribution
   const uint32_t qinf[2] = {t.qinfo[i0], t.qinfo[i0 + 8]};
   const float lse2[2] = {i0 < t.nq ? lse_s[il] * LOG2E : INFINITY, i0 + 8 < t.nq ? lse_s[il + 8] * LOG2E : INFINITY};
   const float del[2] = {del_s[il], del_s[il + 8]};
-  for (int kb = 0; kb < nkb; ++kb) {
-    unsigned char* Ks = KVs + (kb & 1) * 2 * TILE;
+  for (int kb = kb0; kb < kb1; ++kb) {
+    unsigned char* Ks = KVs + ((kb - kb0) & 1) * 2 * TILE;
     unsigned char* Vs = Ks + TILE;
-    if (kb > 0) {
+    if (kb > kb0) {
       cp_async_wait<0>();
       __syncthreads();
     }
-    if (kb + 1 < nkb) {  // (the barrier before this loop / above guarantees the other buffer is no longer read)
-      unsigned char* Kn = KVs + ((kb + 1) & 1) * 2 * TILE;
+    if (kb + 1 < kb1) {  // (the barrier before this loop / above guarantees the other buffer is no longer read)
+      unsigned char* Kn = KVs + ((kb + 1 - kb0) & 1) * 2 * TILE;
       load_tile_async<HD>(Kn, P.K, P.ldk, col0, t.krow_s, (kb + 1) * BKEY);
       load_tile_async<HD>(Kn + TILE, P.V, P.ldv, col0, t.krow_s, (kb + 1) * BKEY);
       cp_async_commit();

@@ -223,15 +223,17 @@ class SelfAttnFn(Function):
 
 
 class CrossAttnFn(Function):
-    """BertCrossAttention core (bert.py:314-340): q [rows,Hd]; kv [B*S, 2*Hd] (k|v) shared by
-    every pass of a sample through (kv_row0, kv_len) ranges; no mask (bert.py:327)."""
+    """BertCrossAttention core (bert.py:314-340): q [rows,Hd]; kv [B*S, 2*Hd] (k|v); no mask (bert.py:327).
+    One problem per SAMPLE: its queries are the text rows of every caption pass (sample-major batch), its keys the
+    sample's media tokens, and `q_key_range` gives each query the key subset of its pass (tva: all, tv: video,
+    ta: audio).  Every K/V row then has exactly one owner, so dK/dV are written directly in the compute dtype."""
 
     @staticmethod
     def forward(ctx, q, kv, spec):
         Hd = spec["H"] * spec["hd"]
         q = q.contiguous()
         o, lse = K.mha_fwd(q, kv[:, :Hd], kv[:, Hd:], spec["P"], spec["H"], spec["hd"], spec["Nq"], spec["max_nk"],
-                           spec["scale"], kv_row0=spec["kv_row0"], kv_len=spec["kv_len"])
+                           spec["scale"], kv_row0=spec["kv_row0"], kv_len=spec["kv_len"], q_key_range=spec.get("q_key_range"))
         ctx.save_for_backward(q, kv, o, lse)
         ctx.spec = spec
         return o
@@ -242,8 +244,14 @@ class CrossAttnFn(Function):
         s = ctx.spec
         Hd = s["H"] * s["hd"]
         dq = torch.empty_like(q)
+        if s.get("kv_exclusive"):
+            dkv = torch.empty_like(kv) if s.get("kv_full") else torch.zeros_like(kv)   # rows outside every range get 0
+            K.mha_bwd(q, kv[:, :Hd], kv[:, Hd:], o, do, lse, dq, s["P"], s["H"], s["hd"], s["Nq"], s["max_nk"], s["scale"],
+                      kv_row0=s["kv_row0"], kv_len=s["kv_len"], q_key_range=s.get("q_key_range"),
+                      dkv_out=(dkv[:, :Hd], dkv[:, Hd:]))
+            return dq, dkv, None
         dkv32 = K.mha_bwd(q, kv[:, :Hd], kv[:, Hd:], o, do, lse, dq, s["P"], s["H"], s["hd"], s["Nq"], s["max_nk"],
-                          s["scale"], kv_row0=s["kv_row0"], kv_len=s["kv_len"])
+                          s["scale"], kv_row0=s["kv_row0"], kv_len=s["kv_len"], q_key_range=s.get("q_key_range"))
         if kv.dtype == torch.float32:
             dkv = dkv32
         else:

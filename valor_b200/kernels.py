@@ -126,17 +126,18 @@ def l2norm_bwd(dy, x, nrm):
 # attention
 # ------------------------------------------------------------------------------------------
 def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None, key_valid=None,
-            causal=None, backend=BACKEND_AUTO):
-    """q: [rows_q, >=H*hd] view, k/v: [rows_kv, >=H*hd] views (may alias one fused buffer)."""
+            causal=None, q_key_range=None, backend=BACKEND_AUTO):
+    """q: [rows_q, >=H*hd] view, k/v: [rows_kv, >=H*hd] views (may alias one fused buffer).
+    q_key_range: int32 [Nq, 2], query i only sees keys lo <= j < hi of its problem."""
     o = torch.empty(q.shape[0], H * hd, device=q.device, dtype=q.dtype)
     lse = torch.empty(P_, H, Nq, device=q.device, dtype=torch.float32)
     _call("valor_mha_fwd", DT(q), P(q), P(k), P(v), _ld(q), _ld(k), _ld(v), P(o), _ld(o), P(lse), P_, H, hd, Nq,
-          max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal), float(scale), backend, ST())
+          max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal), P(q_key_range), float(scale), backend, ST())
     return o, lse
 
 
 def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
-            key_valid=None, causal=None, dkv_out=None, backend=BACKEND_AUTO):
+            key_valid=None, causal=None, dkv_out=None, q_key_range=None, backend=BACKEND_AUTO):
     """dq_out: [rows_q, >=H*hd] view receiving dQ.
     dkv_out=None  -> returns an fp32 [rows_kv, 2*H*hd] buffer with dK|dV accumulated (shared K/V rows: cross-attention);
     dkv_out=(dk_view, dv_view) in the compute dtype -> written directly (each K/V row owned by one problem)."""
@@ -155,7 +156,7 @@ def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=No
         args = (None, None, 0, 0, P(dk), P(dv), _ld(dk))
     _call("valor_mha_bwd", DT(q), P(q), P(k), P(v), P(o), P(do), _ld(q), _ld(k), _ld(v), _ld(o), P(lse), P(delta), P(dq_out),
           _ld(dq_out), *args, P_, H, hd, Nq, max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal),
-          float(scale), backend, ST())
+          P(q_key_range), float(scale), backend, ST())
     return dkv
 
 

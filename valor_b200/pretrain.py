@@ -123,11 +123,11 @@ class VALOR(VALORModel):
             names = [n for n in ("tva", "tv", "ta") if n in caption_task]
             ranges = {"tva": (0, Sv + Sa), "tv": (0, Sv), "ta": (Sv, Sa)}
             npass = len(names)
-            tok_all = txt_input.repeat(npass, 1)
+            tok_all = txt_input.repeat_interleave(npass, 0)            # sample-major: row b*npass + pass
             h = self.multimodal_encoder.encode(tok_all, [True] * npass, media, [ranges[n] for n in names], B)
             logits = self.cls(h)                                                                # every position;
             # labels == -1 rows are ignored.  Every pass shares the same labels, so the mean over all
             # npass*B*T rows equals the reference's mean of per-pass means (pretrain.py:473-479).
-            labels = txt_labels.reshape(-1).repeat(npass)
+            labels = txt_labels.repeat_interleave(npass, 0).reshape(-1)
             loss_dict["caption_loss"] = Fn.XentFn.apply(logits, labels).reshape(())
         return loss_dict
