@@ -146,7 +146,8 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, c
 // rows a warp visits (each lane owns the same columns on every row), then reduced through
 // shared memory and flushed with one atomicAdd per column per CTA into fp32 gradients.
 // ---------------------------------------------------------------------------------------
-template <typename T, int VPL /* float4-groups per lane; N == VPL*128 */, int R /* rows in flight per warp */>
+template <typename T, int VPL /* float4-groups per lane; N == VPL*128 */, int R /* rows in flight per warp */,
+          bool PARAM_GRADS /* accumulate dgamma/dbeta here (8*VPL registers); wide rows use ln_param_grad_kernel instead */>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ dres,
@@ -156,15 +157,18 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   constexpr bool kCacheGamma = VPL <= 4;   // wide rows re-read gamma from L1 instead of pinning 4*VPL registers
-  float ag[VPL][4], ab[VPL][4], gm[kCacheGamma ? VPL : 1][4];
+  constexpr int AV = PARAM_GRADS ? VPL : 1;
+  float ag[AV][4], ab[AV][4], gm[kCacheGamma ? VPL : 1][4];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     if (kCacheGamma) {
       const float4 g = *(const float4*)(gamma + (k * 32 + lane) * 4);
       gm[k][0] = g.x; gm[k][1] = g.y; gm[k][2] = g.z; gm[k][3] = g.w;
     }
+    if (PARAM_GRADS) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
+      for (int e = 0; e < 4; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
+    }
   }
   for (long long row0 = ((long long)blockIdx.x * nwarp + warp) * R; row0 < M; row0 += (long long)gridDim.x * nwarp * R) {
     float fdy[R][VPL][4], fxh[R][VPL][4], mu[R], rs[R], s1[R], s2[R];
@@ -197,8 +201,10 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           fxh[r][k][e] = (fxh[r][k][e] - mu[r]) * rs[r];
-          ag[k][e] += fdy[r][k][e] * fxh[r][k][e];
-          ab[k][e] += fdy[r][k][e];
+          if (PARAM_GRADS) {
+            ag[k][e] += fdy[r][k][e] * fxh[r][k][e];
+            ab[k][e] += fdy[r][k][e];
+          }
           fdy[r][k][e] *= gk[e];  // dy * gamma
           a1 += fdy[r][k][e];
           a2 += fdy[r][k][e] * fxh[r][k][e];
@@ -227,8 +233,9 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
       }
     }
   }
+  if (!PARAM_GRADS) return;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
+  for (int k = 0; k < AV; ++k) {
     const int c = (k * 32 + lane) * 4;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -240,6 +247,40 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     if (dgamma) atomicAdd(&dgamma[i], sh[i]);
     if (dbeta) atomicAdd(&dbeta[i], sh[N + i]);
+  }
+}
+
+// dgamma += sum_r dy*xhat, dbeta += sum_r dy for wide rows: CTA = 128-column panel x row range (the panel re-reads
+// dy and x, which the dx pass has just pulled through L2)
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int N,
+                     int rows_per_block) {
+  __shared__ float sh[2][8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 128 + lane * 4;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    Vec4<T> a, b; a.load(dy + r * N + c0); b.load(x + r * N + c0);
+    float fd[4], fx[4]; a.get(fd); b.get(fx);
+    const float mu = mean[r], rs = rstd[r];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ag[e] += fd[e] * ((fx[e] - mu) * rs); ab[e] += fd[e]; }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[0][warp][lane * 4 + e] = ag[e]; sh[1][warp][lane * 4 + e] = ab[e]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tg += sh[0][i][threadIdx.x]; tb += sh[1][i][threadIdx.x]; }
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (dgamma) atomicAdd(&dgamma[col], tg);
+    if (dbeta) atomicAdd(&dbeta[col], tb);
   }
 }
 
@@ -289,13 +330,21 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
   int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)2 * N * sizeof(float);
-#define LN_BWD_CASE(V, RR)                                                                                      \
+#define LN_BWD_CASE(V, RR, PG)                                                                                  \
   case V * 128:                                                                                                 \
-    layernorm_bwd_kernel<T, V, RR><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,       \
-                                                             (const T*)dres, (T*)dx, dgamma, dbeta, M, N);      \
+    layernorm_bwd_kernel<T, V, RR, PG><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,   \
+                                                                 (const T*)dres, (T*)dx, dgamma, dbeta, M, N);  \
+    if (!PG && (dgamma || dbeta)) {                                                                             \
+      if (check_launch("layernorm_bwd_kernel")) return 1;                                                       \
+      long long rpb = (M * (N / 128) + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);              \
+      if (rpb < 64) rpb = 64;                                                                                   \
+      dim3 g2(N / 128, (unsigned)((M + rpb - 1) / rpb));                                                        \
+      ln_param_grad_kernel<T><<<g2, 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, dgamma, dbeta, M, N, (int)rpb); \
+    }                                                                                                           \
     break;
   switch (N) {
-    LN_BWD_CASE(1, 4) LN_BWD_CASE(2, 2) LN_BWD_CASE(4, 1) LN_BWD_CASE(6, 1) LN_BWD_CASE(8, 1) LN_BWD_CASE(16, 1)
+    LN_BWD_CASE(1, 4, true) LN_BWD_CASE(2, 2, true) LN_BWD_CASE(4, 1, true) LN_BWD_CASE(6, 1, true)
+    LN_BWD_CASE(8, 1, false) LN_BWD_CASE(16, 1, false)
     default:
       layernorm_bwd_generic_kernel<T><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,
                                                                 (const T*)dres, (T*)dx, dgamma, dbeta, M, N);
