@@ -527,10 +527,20 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
     lse_s[i] = ok ? P.lse[((size_t)p * P.H + h) * P.Nq + i] * LOG2E : INFINITY;  // log2 domain; +inf kills padding
     del_s[i] = ok ? delta[((size_t)p * P.H + h) * P.Nq + i] : 0.f;
   }
+  // query blocks whose visible key range touches this key block (all of them without per-query ranges)
+  const int nqb = (t.nq + BQ - 1) / BQ;
+  uint32_t qmask = 0;
+  for (int q = 0; q < nqb && q < 32; ++q) {
+    int a, b;
+    key_block_span(t, q * BQ, a, b);
+    if (kb >= a && kb < b) qmask |= 1u << q;
+  }
+  if (nqb > 32) qmask = 0xffffffffu;   // (never on this path: Nq <= 2048)
   load_tile_async<HD>(Ks, P.K, P.ldk, col0, t.krow_s, kb * BKEY);
   load_tile_async<HD>(Vs, P.V, P.ldv, col0, t.krow_s, kb * BKEY);
-  load_tile_async<HD>(QDs, P.Q, P.ldq, col0, t.qrow_s, 0);
-  load_tile_async<HD>(QDs + TILE, P.dO, P.ldo, col0, t.qrow_s, 0);
+  const int qb_first = qmask ? __ffs(qmask) - 1 : 0;
+  load_tile_async<HD>(QDs, P.Q, P.ldq, col0, t.qrow_s, qb_first * BQ);
+  load_tile_async<HD>(QDs + TILE, P.dO, P.ldo, col0, t.qrow_s, qb_first * BQ);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -549,18 +559,21 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
   const float sc = P.scale, sc2 = P.scale * LOG2E;
   const int j0 = kb * BKEY + warp * 16 + g;  // keys j0 and j0+8 (padding keys: K/V rows are zero, results dropped)
   const uint32_t kinf[2] = {t.kinfo[j0], t.kinfo[j0 + 8]};
-  const int nqb = (t.nq + BQ - 1) / BQ;
-  for (int qb = 0; qb < nqb; ++qb) {
-    unsigned char* Qs = QDs + (qb & 1) * 2 * TILE;
+  uint32_t todo = qmask;
+  for (int it = 0; todo != 0; ++it) {
+    const int qb = __ffs(todo) - 1;
+    todo &= todo - 1;
+    unsigned char* Qs = QDs + (it & 1) * 2 * TILE;
     unsigned char* dOs = Qs + TILE;
-    if (qb > 0) {
+    if (it > 0) {
       cp_async_wait<0>();
       __syncthreads();
     }
-    if (qb + 1 < nqb) {
-      unsigned char* Qn = QDs + ((qb + 1) & 1) * 2 * TILE;
-      load_tile_async<HD>(Qn, P.Q, P.ldq, col0, t.qrow_s, (qb + 1) * BQ);
-      load_tile_async<HD>(Qn + TILE, P.dO, P.ldo, col0, t.qrow_s, (qb + 1) * BQ);
+    if (todo != 0) {   // prefetch the next relevant query block into the other buffer
+      const int qn = __ffs(todo) - 1;
+      unsigned char* Qn = QDs + ((it + 1) & 1) * 2 * TILE;
+      load_tile_async<HD>(Qn, P.Q, P.ldq, col0, t.qrow_s, qn * BQ);
+      load_tile_async<HD>(Qn + TILE, P.dO, P.ldo, col0, t.qrow_s, qn * BQ);
       cp_async_commit();
     }
 #pragma unroll 1
@@ -672,6 +685,7 @@ template <int HD, bool WINDOW>
 static int launch_bwd(const AttnParams& P, float* delta, int Pn, int nq, int max_nk, cudaStream_t st) {
   constexpr int PITCH = HD * 2 + 16;
   const int nq_pad = pad64(nq), nk_pad = pad64(max_nk);
+  VALOR_REQUIRE(nq <= 2048, "attention backward: at most 2048 queries per problem (query-block bitmask)");
   size_t n_rel = 0;
   if (WINDOW) n_rel = (size_t)(2 * P.win.WD - 1) * (2 * P.win.WH - 1) * (2 * P.win.WW - 1);
   const size_t tb = table_bytes<HD, WINDOW>(P, nq_pad, nk_pad);

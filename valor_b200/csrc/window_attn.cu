@@ -84,6 +84,14 @@ __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_grou
 __device__ __forceinline__ int small_div(int i, int inv) { return (int)(((unsigned)i * (unsigned)inv) >> 20); }
 __host__ __device__ __forceinline__ int small_inv(int d) { return (int)(((1u << 20) + d - 1) / d); }
 
+// dq warp w of n_dq owns the contiguous 16-query blocks [start, start + cnt): contiguous rows have a narrow span of
+// query codes, so the warp's private gradient table only needs  span + maxcode + 1  slots instead of 2*maxcode + 1.
+__host__ __device__ __forceinline__ void dq_range(int w, int n_dq, int nrb, int& start, int& cnt) {
+  const int base = nrb / n_dq, rem = nrb % n_dq;
+  start = w * base + (w < rem ? w : rem);
+  cnt = base + (w < rem ? 1 : 0);
+}
+
 struct WinParams {
   const bf16* qkv; long long ld;   // [tokens, 3C]: Q | K | V
   bf16* O; long long ldo;          // forward output / backward: saved output
@@ -95,8 +103,9 @@ struct WinParams {
   int heads;
   int NP;                          // N rounded up to 16
   int n_used, maxcode, center;     // bias slots reachable inside one window: [center-maxcode, center+maxcode]
-  int tab_stride;                  // bytes between per-warp gradient tables (n_used*4 rounded up to 16)
+  int tab_stride;                  // bytes of the bias slice (n_used*4 rounded up to 16)
   int n_dq_warps;                  // backward: warps 0..n_dq_warps-1 take the query blocks, the rest the key blocks
+  int gtab_bytes;                  // backward: bytes of one dq warp's private gradient table (see dq_range)
   WindowIndex win;
 };
 
@@ -150,8 +159,8 @@ __device__ __forceinline__ bool win_build_tables(const WinParams& P, int p, int 
       S.kcode[i] = (uint32_t)(4 * code);
       S.qreg[i] = reg;
     } else {
-      S.qrow[i] = -1;
-      S.qcode[i] = (uint32_t)(4 * P.maxcode); S.kcode[i] = 0u; S.qreg[i] = 0u;
+      S.qrow[i] = -1;   // padding rows reuse the last token's query code: their (zero) gradient folds stay inside the
+      S.qcode[i] = (uint32_t)(8 * P.maxcode); S.kcode[i] = 0u; S.qreg[i] = 0u;   // owning warp's private table range
     }
   }
   const float* src = ix.table + (size_t)(P.center - P.maxcode) * ix.heads + h;
@@ -191,12 +200,12 @@ struct Lane {
   }
 };
 
-static inline size_t win_smem_bytes(int NP, int n_used, bool bwd, int n_dq_warps) {
+static inline size_t win_smem_bytes(int NP, int n_used, bool bwd, int n_dq_warps, int gtab_bytes = 0) {
   size_t b = (size_t)(bwd ? 4 : 3) * NP * ROWB;   // Q K V (dO)
   b += (size_t)4 * NP * 4;                        // qrow qcode kcode qreg
   const size_t tab = ((size_t)n_used * 4 + 15) / 16 * 16;
   b += tab;                                       // bias slice
-  if (bwd) b += (size_t)2 * NP * 4 + (size_t)n_dq_warps * (tab + 16 * 40 * 4 + 16);   // {lse, -delta}, per-warp tables + staging + parking word
+  if (bwd) b += (size_t)2 * NP * 4 + 128 + (size_t)n_dq_warps * (gtab_bytes + 16 * 40 * 4 + 16);   // {lse, -delta}, table ranges, per-warp tables + staging + parking word
   return b + 16;
 }
 
@@ -701,14 +710,15 @@ __device__ __forceinline__ void bwd_dkv_unit(const WinParams& P, const Smem& S, 
   }
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(448, 1)
 window_bwd_kernel(WinParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int NP = P.NP;
   const Smem S = carve(smem, NP, true);
   float* ln_sm = (float*)((unsigned char*)S.tab + P.tab_stride);    // per query {natural-log lse (+inf on padding), -delta}
-  unsigned char* priv = (unsigned char*)(ln_sm + 2 * NP);            // per dq warp: [tab_stride] table + [16][40] staging + parking word
-  const int priv_stride = P.tab_stride + 16 * 40 * 4 + 16;
+  int* wrange = (int*)(ln_sm + 2 * NP);                              // [16][2] first / last slot byte offset of each dq warp's table
+  unsigned char* priv = (unsigned char*)(wrange + 32);               // per dq warp: [gtab_bytes] table + [16][40] staging + parking word
+  const int priv_stride = P.gtab_bytes + 16 * 40 * 4 + 16;
   const int p = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int C = P.heads * HD, col0 = h * HD;
@@ -754,10 +764,17 @@ window_bwd_kernel(WinParams P) {
   const uint32_t ln_s = sm_addr(ln_sm);
   const int nq = P.n_dq_warps;
   if (warp < nq) {
-    const uint32_t gtab_s = sm_addr(priv + warp * priv_stride);
-    const uint32_t stg_s = gtab_s + P.tab_stride;
-    if (masked) { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<true>(P, S, L, h, rb, ln_s, gtab_s, stg_s); }
-    else        { for (int rb = warp; rb < nrb; rb += nq) bwd_dq_unit<false>(P, S, L, h, rb, ln_s, gtab_s, stg_s); }
+    int start, cnt;
+    dq_range(warp, nq, nrb, start, cnt);
+    // slot byte offsets this warp can touch: [qcode(first row) - 4*maxcode, qcode(last row)] (codes grow with the index)
+    const int lo = (int)S.qcode[start * 16] - 4 * P.maxcode;
+    const int hi = (int)S.qcode[min((start + cnt) * 16, N) - 1];
+    if (L.lane == 0) { wrange[2 * warp] = lo; wrange[2 * warp + 1] = hi; }
+    const uint32_t phys = sm_addr(priv + warp * priv_stride);
+    const uint32_t gtab_s = phys - (uint32_t)lo;   // virtual base: slot byte offset b lives at phys + (b - lo)
+    const uint32_t stg_s = phys + P.gtab_bytes;
+    if (masked) { for (int rb = start; rb < start + cnt; ++rb) bwd_dq_unit<true>(P, S, L, h, rb, ln_s, gtab_s, stg_s); }
+    else        { for (int rb = start; rb < start + cnt; ++rb) bwd_dq_unit<false>(P, S, L, h, rb, ln_s, gtab_s, stg_s); }
   } else {
     const int nk = nwarps - nq;
     if (masked) { for (int jb = warp - nq; jb < nrb; jb += nk) bwd_dkv_unit<true>(P, S, L, h, jb, ln_s); }
@@ -768,7 +785,10 @@ window_bwd_kernel(WinParams P) {
     const int r0 = P.center - P.maxcode;
     for (int r = threadIdx.x; r < P.n_used; r += blockDim.x) {
       float acc = 0.f;
-      for (int w = 0; w < nq; ++w) acc += ((const float*)(priv + w * priv_stride))[r];
+      for (int w = 0; w < nq; ++w) {
+        const int lo = wrange[2 * w], hi = wrange[2 * w + 1];
+        if (4 * r >= lo && 4 * r <= hi) acc += *(const float*)(priv + w * priv_stride + (4 * r - lo));
+      }
       if (acc != 0.f) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], acc);
     }
   }
@@ -798,18 +818,36 @@ static int fwd_warps(int nrb) {
   return (nrb + per - 1) / per;
 }
 
-// backward: split up to 12 warps between query blocks (dQ + bias gradient, ~1.35x the work of a key block) and key
+// bytes of the largest private gradient table when n_dq warps share the query blocks contiguously
+static int gtab_bytes_for(const WindowIndex& ix, int NP, int maxcode, int n_dq) {
+  const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
+  auto code = [&](int i) { return (i / (ix.wh * ix.ww)) * cH + ((i / ix.ww) % ix.wh) * cW + i % ix.ww; };
+  const int nrb = NP / 16;
+  int worst = 0;
+  for (int w = 0; w < n_dq; ++w) {
+    int start, cnt;
+    dq_range(w, n_dq, nrb, start, cnt);
+    if (cnt == 0) continue;
+    const int last = std::min((start + cnt) * 16, ix.N) - 1;
+    worst = std::max(worst, 4 * (code(last) - code(start * 16)) + 4 * maxcode + 4);
+  }
+  return (worst + 15) / 16 * 16;
+}
+
+// backward: split up to 14 warps between query blocks (dQ + bias gradient, ~1.7x the work of a key block) and key
 // blocks (dK, dV) so that the slower group finishes earliest; every dq warp needs a private table in shared memory
-static bool bwd_warps(int NP, int n_used, int& n_dq, int& n_dkv) {
+static bool bwd_warps(const WindowIndex& ix, int NP, int n_used, int maxcode, int& n_dq, int& n_dkv, int& gtab_bytes) {
   const int nrb = NP / 16;
   double best = 1e30;
-  n_dq = n_dkv = 0;
-  for (int q = 1; q <= 13; ++q)
-    for (int k = 1; q + k <= 12; ++k) {
-      if (win_smem_bytes(NP, n_used, true, q) > kSmemLimit) continue;
-      const double cost = std::max(1.35 * ((nrb + q - 1) / q), 1.0 * ((nrb + k - 1) / k)) + 1e-3 * (q + k);
-      if (cost < best) { best = cost; n_dq = q; n_dkv = k; }
+  n_dq = n_dkv = gtab_bytes = 0;
+  for (int q = 1; q <= 13 && q <= nrb; ++q) {
+    const int gb = gtab_bytes_for(ix, NP, maxcode, q);
+    if (win_smem_bytes(NP, n_used, true, q, gb) > kSmemLimit) continue;
+    for (int k = 1; q + k <= 14; ++k) {
+      const double cost = std::max(1.7 * ((nrb + q - 1) / q), 1.0 * ((nrb + k - 1) / k)) + 1e-3 * (q + k);
+      if (cost < best) { best = cost; n_dq = q; n_dkv = k; gtab_bytes = gb; }
     }
+  }
   return n_dq > 0;
 }
 
@@ -819,8 +857,8 @@ bool window_cta_eligible(const WindowIndex& ix, int hd) {
   win_geometry(P, ix, 1);
   if (4 * (2 * P.maxcode + 1) >= 65536) return false;
   if (ix.wh * ix.ww > 256) return false;   // small_div range
-  int q, k;
-  return win_smem_bytes(P.NP, P.n_used, false, 0) <= kSmemLimit && bwd_warps(P.NP, P.n_used, q, k);
+  int q, k, gb;
+  return win_smem_bytes(P.NP, P.n_used, false, 0) <= kSmemLimit && bwd_warps(ix, P.NP, P.n_used, P.maxcode, q, k, gb);
 }
 
 int window_cta_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
@@ -844,10 +882,15 @@ int window_cta_bwd(const WindowIndex& ix, const void* qkv, long long ld, const v
   win_geometry(P, ix, H);
   P.qkv = (const bf16*)qkv; P.ld = ld; P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.scale = scale;
   P.dO = (const bf16*)dO; P.dqkv = (bf16*)dqkv; P.lddqkv = lddqkv; P.dtable = dtable;
+  static int no_dtab = -1;   // VALOR_WINDOW_NO_DTAB=1: skip the bias-table gradient (measurement of the fold's cost only)
+  if (no_dtab < 0) { const char* e = getenv("VALOR_WINDOW_NO_DTAB"); no_dtab = e ? atoi(e) : 0; }
+  if (no_dtab) P.dtable = nullptr;
   int n_dq = 0, n_dkv = 0;
-  VALOR_REQUIRE(bwd_warps(P.NP, P.n_used, n_dq, n_dkv), "window_cta_bwd: window does not fit in shared memory");
+  int gb = 0;
+  VALOR_REQUIRE(bwd_warps(ix, P.NP, P.n_used, P.maxcode, n_dq, n_dkv, gb), "window_cta_bwd: window does not fit in shared memory");
   P.n_dq_warps = n_dq;
-  const size_t smem = win_smem_bytes(P.NP, P.n_used, true, n_dq);
+  P.gtab_bytes = gb;
+  const size_t smem = win_smem_bytes(P.NP, P.n_used, true, n_dq, gb);
   static size_t attr = 0;
   if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   window_bwd_kernel<<<dim3(Pn, H), (n_dq + n_dkv) * 32, smem, st>>>(P);
