@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TASK = "pt_contra%tva%tv%ta_caption%tva%tv%ta"
+# mean DRAM traffic of one tcgen05 GEMM launch of the C2 step, from profiles/launches_r1_final.txt
+# (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the 888 GEMM launches of one step: 117.82 GB)
+GEMM_DRAM_BYTES_PER_LAUNCH = 132.68e6
 FLOPS_PER_SAMPLE = 1178.8e9  # fwd+bwd matmul FLOPs / sample at F8 A2 T32
 
 
@@ -291,7 +294,9 @@ def main():
         n_t = sum(1 for r in recs if r[3])
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_kind": f"{peak_kind} (sustained bf16)",
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if args.geom == "base" and B == 32 else None,
+                "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's GEMM launches)",
+                "peak_kind": f"{peak_kind} (sustained bf16)",
                 "launches_per_step": n_t, "gemm_ms_per_step": t_ms, "gemm_tflop_per_step": fl / 1e12,
                 "gemm_share_of_step": None}
 
