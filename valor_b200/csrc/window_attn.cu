@@ -437,17 +437,16 @@ __device__ __forceinline__ void dq_sweep(const Lane& L, DqRow& R, int left, floa
   constexpr int CO = SUB * 128;         // code-word offset
   const int npair = TAIL ? min(2, (left + 15) >> 4) : 2;
   float s[4][4], dp[4][4];
-  uint32_t kfr[2][2][4];   // K fragments of the sweep [pair][ks]: reused (transposed in registers) for dQ += dS.K
   static_for<2>([&](auto pr_) {
     constexpr int pr = decltype(pr_)::value;
     if (!TAIL || pr < npair) {
       uint32_t b[4];
-      ldsm4_o<KO + pr * 16 * ROWB>(kfr[pr][0], R.kb0);
-      mma_init(s[pr * 2], R.qf[0], kfr[pr][0], 0.f, 0.f, 0.f, 0.f);
-      mma_init(s[pr * 2 + 1], R.qf[0], kfr[pr][0] + 2, 0.f, 0.f, 0.f, 0.f);
-      ldsm4_o<KO + pr * 16 * ROWB>(kfr[pr][1], R.kb1);
-      mma_acc(s[pr * 2], R.qf[1], kfr[pr][1]);
-      mma_acc(s[pr * 2 + 1], R.qf[1], kfr[pr][1] + 2);
+      ldsm4_o<KO + pr * 16 * ROWB>(b, R.kb0);
+      mma_init(s[pr * 2], R.qf[0], b, 0.f, 0.f, 0.f, 0.f);
+      mma_init(s[pr * 2 + 1], R.qf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
+      ldsm4_o<KO + pr * 16 * ROWB>(b, R.kb1);
+      mma_acc(s[pr * 2], R.qf[1], b);
+      mma_acc(s[pr * 2 + 1], R.qf[1], b + 2);
       ldsm4_o<KO + pr * 16 * ROWB>(b, R.vb0);   // dP - delta: the accumulator starts at -delta_i
       mma_init(dp[pr * 2], R.dof[0], b, R.ndel[0], R.ndel[0], R.ndel[1], R.ndel[1]);
       mma_init(dp[pr * 2 + 1], R.dof[0], b + 2, R.ndel[0], R.ndel[0], R.ndel[1], R.ndel[1]);
@@ -484,15 +483,13 @@ __device__ __forceinline__ void dq_sweep(const Lane& L, DqRow& R, int left, floa
   static_for<2>([&](auto kk_) {
     constexpr int kk = decltype(kk_)::value;
     if (!TAIL || kk < npair) {
-      // K as the B operand of dQ += dS.K is the 8x8-transposed image of the fragments fetched for S = Q.K^T:
-      // kfr[kk][ks] = {keys 0-7 | dims 16ks..+7, keys 0-7 | dims +8..+15, keys 8-15 | dims ..+7, keys 8-15 | dims +8..}
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const uint32_t b0[2] = {movm_t(kfr[kk][ks][0]), movm_t(kfr[kk][ks][2])};
-        const uint32_t b1[2] = {movm_t(kfr[kk][ks][1]), movm_t(kfr[kk][ks][3])};
-        mma_acc(R.dq[ks * 2], dsf[kk], b0);
-        mma_acc(R.dq[ks * 2 + 1], dsf[kk], b1);
-      }
+      uint32_t b[4];
+      ldsm4t_o<KO + kk * 16 * ROWB>(b, R.kt0);
+      mma_acc(R.dq[0], dsf[kk], b);
+      mma_acc(R.dq[1], dsf[kk], b + 2);
+      ldsm4t_o<KO + kk * 16 * ROWB>(b, R.kt1);
+      mma_acc(R.dq[2], dsf[kk], b);
+      mma_acc(R.dq[3], dsf[kk], b + 2);
     }
   });
   if (want_dtab) {
@@ -593,14 +590,12 @@ __device__ __forceinline__ void dkv_sweep(const Lane& L, DkvRow& R, int left, fl
   constexpr int LO = SUB * 256;
   const int npair = TAIL ? min(2, (left + 15) >> 4) : 2;
   float s[4][4], dp[4][4];   // rows = keys (g, g+8), cols = queries
-  float4 ln4[4];             // {lse, -delta} of this lane's two query columns, per n-tile
   static_for<2>([&](auto pr_) {
     constexpr int pr = decltype(pr_)::value;
     if (!TAIL || pr < npair) {
       uint32_t b[4];
-      ln4[pr * 2] = ld_v4f32_o<LO + pr * 128>(R.ln);
-      ln4[pr * 2 + 1] = ld_v4f32_o<LO + pr * 128 + 64>(R.ln);
-      const float4 l0 = ln4[pr * 2], l1 = ln4[pr * 2 + 1];
+      const float4 l0 = ld_v4f32_o<LO + pr * 128>(R.ln);        // {lse, -delta} of the two query columns, n-tile 2*pr
+      const float4 l1 = ld_v4f32_o<LO + pr * 128 + 64>(R.ln);   // n-tile 2*pr + 1
       ldsm4_o<QO + pr * 16 * ROWB>(b, R.qb0);
       mma_init(s[pr * 2], R.kf[0], b, 0.f, 0.f, 0.f, 0.f);
       mma_init(s[pr * 2 + 1], R.kf[0], b + 2, 0.f, 0.f, 0.f, 0.f);
@@ -621,7 +616,7 @@ __device__ __forceinline__ void dkv_sweep(const Lane& L, DkvRow& R, int left, fl
     float pv[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
     if (!TAIL || (nt >> 1) < npair) {
       const uint2 qc = ld_v2u32_o<CO + nt * 32>(R.qc);       // two consecutive queries (columns of S^T)
-      const float4 l4 = ln4[nt];                             // lse = +inf on padding queries -> p = 0
+      const float4 l4 = ld_v4f32_o<LO + nt * 64>(R.ln);      // lse = +inf on padding queries -> p = 0
       uint2 qr = make_uint2(0u, 0u);
       if (MASKED) qr = ld_v2u32_o<CO + nt * 32>(R.qr);
       const float nl[2] = {-l4.x * kLog2e, -l4.z * kLog2e};
