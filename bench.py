@@ -349,18 +349,36 @@ def main():
     launches = graph_launches if graph is not None else (K.launch_count - l0) // args.steps
     log(f"timed: {ms_step:.2f} ms/step, {launches} launches/step")
 
+    # End to end: every step's inputs come from pinned host memory and the losses go back to the host.  Like the
+    # reference's PrefetchLoader (data/loader.py:154-206) the H2D copy of step i+1 runs on a side stream while step i
+    # computes; it lands in a staging buffer and is moved into the graph's static inputs (device-to-device, ~0.1 ms)
+    # at the start of its step.
+    copy_stream = torch.cuda.Stream()
+    flat_res = {"video": resident["video_pixels"], "audio": resident["audio_spectrograms"],
+                "tokens": resident["txt_tokens"]["bert_tokens"], "mi": resident["caption_mask"][0],
+                "ml": resident["caption_mask"][1]}
+    staging = {k: torch.empty_like(v) for k, v in flat_res.items()}
+    ev_h2d, ev_taken = torch.cuda.Event(), torch.cuda.Event()
+
+    def prefetch():
+        copy_stream.wait_event(ev_taken)                 # the previous contents of `staging` have been consumed
+        with torch.cuda.stream(copy_stream):
+            for k, v in staging.items():
+                v.copy_(pinned[k], non_blocking=True)
+            ev_h2d.record(copy_stream)
+
     def e2e_step():
-        if graph is not None:   # H2D from pinned host memory INTO the graph's static input tensors
-            resident["video_pixels"].copy_(pinned["video"], non_blocking=True)
-            resident["audio_spectrograms"].copy_(pinned["audio"], non_blocking=True)
-            resident["txt_tokens"]["bert_tokens"].copy_(pinned["tokens"], non_blocking=True)
-            resident["caption_mask"][0].copy_(pinned["mi"], non_blocking=True)
-            resident["caption_mask"][1].copy_(pinned["ml"], non_blocking=True)
-            losses = train_step(resident)
-        else:
-            losses = train_step(to_device())
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_h2d)                           # this step's inputs have arrived
+        for k, v in flat_res.items():
+            v.copy_(staging[k], non_blocking=True)
+        ev_taken.record(cur)
+        prefetch()                                       # next step's H2D overlaps this step's compute
+        losses = train_step(resident) if graph is not None else eager_step(resident)
         return {k: v.item() for k, v in losses.items()}     # D2H read of the step's result
 
+    ev_taken.record(torch.cuda.current_stream())
+    prefetch()
     e2e_step()
     ms_e2e, loss_vals = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -377,7 +395,8 @@ def main():
                        "l2": "inputs larger than L2 (154 MB pixels/step), weights+activations >> 126 MB",
                        "geom": args.geom},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 4 * len(loss_vals)},
+                    "d2h_bytes_per_step": 4 * len(loss_vals),
+                    "pipeline": "H2D of step i+1 on a copy stream during step i (PrefetchLoader semantics), losses read back every step"},
             "gpu_launches": launches, "cuda_graph": graph is not None, "clocks": clocks, "losses": loss_vals,
             "step_mfu": FLOPS_PER_SAMPLE * B / (ms_step * 1e-3) / (peak_tf * 1e12) if args.geom == "base" else None}
     if roof:
