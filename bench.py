@@ -265,10 +265,13 @@ def main():
         train_step(resident)
         torch.cuda.synchronize()
         log(f"eager warmup step {i} done")
-    # ---- roofline pass: CUDA events around every GEMM launch of one more step (outside the timed region)
+    # ---- roofline pass (outside the timed region): CUDA events around every GEMM launch of one more step.  With
+    # graphs on, the step is captured a second time with `external` events as event-record nodes, so the brackets see
+    # back-to-back kernels exactly as in the timed replay (eager brackets also contain the host launch gap).
     roof = None
     peak_tf, peak_hbm, peak_kind = peaks()
-    if not args.no_roofline:   # every rank runs the probe step (it contains the step's collectives); rank 0 reports
+
+    def roofline_pass(run_step, in_graph):
         recs = []
         orig = K.gemm
 
@@ -276,29 +279,30 @@ def main():
             M, Kd = (a.shape if kw.get("a_kmajor", True) else (a.shape[1], a.shape[0]))
             N = b.shape[0] if kw.get("b_kmajor", True) else b.shape[1]
             tensor = a.dtype == torch.bfloat16 and N >= 8 and Kd >= 8 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
+            s_, e_ = (torch.cuda.Event(enable_timing=True, external=in_graph) for _ in range(2))
+            s_.record()
             r = orig(a, b, **kw)
-            e.record()
-            recs.append((2.0 * M * N * Kd, s, e, tensor))
+            e_.record()
+            recs.append((2.0 * M * N * Kd, s_, e_, tensor))
             return r
 
         K.gemm = gemm_probe
         try:
-            train_step(resident)
-            torch.cuda.synchronize()
+            run_step()
         finally:
             K.gemm = orig
-        t_ms = sum(s.elapsed_time(e) for f, s, e, t in recs if t)
-        fl = sum(f for f, s, e, t in recs if t)
+        torch.cuda.synchronize()
+        t_ms = sum(s_.elapsed_time(e_) for f, s_, e_, t in recs if t)
+        fl = sum(f for f, s_, e_, t in recs if t)
         n_t = sum(1 for r in recs if r[3])
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if args.geom == "base" and B == 32 else None,
+        return {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if args.geom == "base" and B == 32 else None,
                 "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's GEMM launches)",
-                "peak_kind": f"{peak_kind} (sustained bf16)",
-                "launches_per_step": n_t, "gemm_ms_per_step": t_ms, "gemm_tflop_per_step": fl / 1e12,
-                "gemm_share_of_step": None}
+                "peak_kind": f"{peak_kind} (sustained bf16)", "timing": "CUDA events inside a captured graph" if in_graph else
+                "CUDA events, eager launches", "launches_per_step": n_t, "gemm_ms_per_step": t_ms,
+                "gemm_tflop_per_step": fl / 1e12, "gemm_share_of_step": None}
 
     # ---- capture the whole step (forward, backward, all-reduce, clip, AdamW) in one CUDA graph: the C ABI
     # never syncs or allocates, so ~2000 launches replay without Python / launch latency
@@ -332,11 +336,29 @@ def main():
                 graph.replay()
                 return static_losses
             log(f"CUDA graph captured: {graph_launches} ABI launches per step")
+            if not args.no_roofline:   # every rank: the probed step carries the step's collectives
+                try:
+                    probe = torch.cuda.CUDAGraph()
+
+                    def captured_probe():
+                        with torch.cuda.graph(probe):
+                            body(resident)
+                        probe.replay()
+                        torch.cuda.synchronize()
+                        probe.replay()        # the brackets keep the times of the last replay
+                    roof = roofline_pass(captured_probe, True)
+                    del probe
+                except Exception as ex:  # pragma: no cover
+                    log(f"in-graph roofline pass failed ({type(ex).__name__}: {ex}); using eager brackets")
+                    torch.cuda.synchronize()
+                    roof = roofline_pass(lambda: eager_step(resident), False)
         except Exception as ex:  # pragma: no cover
             log(f"CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly")
             graph = None
             train_step = eager_step
             torch.cuda.synchronize()
+    if roof is None and not args.no_roofline:
+        roof = roofline_pass(lambda: eager_step(resident), False)
     for i in range(max(args.warmup, 3)):
         train_step(resident)
         torch.cuda.synchronize()
