@@ -39,6 +39,25 @@ FLOPS_PER_SAMPLE = 1178.8e9  # fwd+bwd matmul FLOPs / sample at F8 A2 T32 (SURVE
 T0 = time.time()
 
 
+# stdout carries exactly one JSON line: keep a private handle to it and point fd 1 at stderr, so banners printed by
+# native libraries (NCCL prints its version on stdout) cannot end up in front of the result
+_RESULT_OUT = None
+
+
+def reserve_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    reserve_stdout()
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 def log(msg):
     print(f"[bench {time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
@@ -179,7 +198,7 @@ def main_reference(args):
                                  f"(samples/s is per-sample throughput; B={args.batch} would take minutes per step on CPU)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -187,6 +206,7 @@ def main_reference(args):
 # --------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    reserve_stdout()
     if args.impl == "reference":
         return main_reference(args)
     import torch
@@ -207,9 +227,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout is reserved for the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     geom = synth.BASE if args.geom == "base" else synth.TINY
     B, F, A, T = args.batch, args.frames, args.clips, args.tokens
@@ -433,7 +450,7 @@ def main():
         log("cpu baseline done")
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         # a captured graph holds NCCL work: tearing the process group down under it can hang, so drain and leave
         torch.cuda.synchronize()
