@@ -84,7 +84,11 @@ int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm,
  * Nq query rows starting at q_row0[p] (NULL: p*Nq) of Q and kv_len[p] (NULL: max_nk) key rows
  * starting at kv_row0[p] (NULL: p*max_nk) of K/V; head h occupies columns [h*hd,(h+1)*hd).
  * scores = q.k^T * scale + mask, mask = -10000 where key_valid[p,j]==0 or (causal[p] && j>i)
- * (bert.py:869-885).  lse [P,H,Nq] fp32 is saved for the backward.
+ * (bert.py:869-885).  q_key_range (NULL or int32 [Nq][2]): query i only sees keys lo <= j < hi of its problem; the
+ * others do not exist for it (excluded from the softmax, not -10000).  This is how the three caption passes of one
+ * sample (tva / tv / ta, pretrain.py:455-479: same text rows, video+audio / video / audio media tokens as
+ * cross-attention source, bert.py:450) run as ONE problem over the sample's media tokens.
+ * lse [P,H,Nq] fp32 is saved for the backward.
  * Backward: dQ written.  dK/dV either accumulate (+=) into fp32 [rows, H*hd] buffers the caller zero-fills
  * (dK/dV: K/V rows shared by several problems add up — cross-attention), or, when every K/V row belongs to
  * exactly one problem (self-attention), are written directly in the compute dtype to dK_lp/dV_lp (pitch
