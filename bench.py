@@ -211,7 +211,7 @@ def main():
         return main_reference(args)
     import torch
     import torch.distributed as dist
-    from oracle import synth  # seeded synthetic weights/batch only (not the checker)
+    from valor_b200 import synthetic as synth   # seeded synthetic weights / batch (the GPU arm never touches oracle/)
     from valor_b200 import kernels as K
     from valor_b200.distributed import allreduce_grads
     from valor_b200.optim import get_lr_sched
