@@ -1,7 +1,7 @@
-// valor_b200 — tensor-core flash attention (bf16, fp32 accumulate / softmax) for the three
-// attention shapes of the step: VideoSwin shifted-window attention (N<=392 keys, hd 32),
-// BERT/AST self attention (32..129 tokens, hd 64) and BERT cross attention (32 queries x
-// 258..650 media keys, hd 64).  S and P never leave the SM: scores live in mma accumulators,
+// valor_b200 — key-blocked tensor-core flash attention (bf16, fp32 accumulate / softmax): BERT/AST
+// self attention (32..129 tokens, hd 64), BERT cross attention (the 3 x 32 caption-pass queries of a
+// sample x its 650 media keys with per-query key ranges, hd 64), and the fallback for window shapes
+// window_attn.cu does not take (hd 64).  S and P never leave the SM: scores live in mma accumulators,
 // the backward recomputes them from the saved log-sum-exp (the reference materialises the full
 // softmax map for autograd: ~19.5 GB per step over the 24 Swin blocks).
 //

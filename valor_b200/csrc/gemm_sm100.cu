@@ -10,9 +10,11 @@
 //
 // Design: persistent, warp-specialised. warp0 = TMA producer (cp.async.bulk.tensor, 128B
 // swizzle), warp1 = single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 in,
-// fp32 accumulate in TMEM, 2 accumulator stages), warp2 = TMEM allocator, warps4-7 =
-// epilogue (tcgen05.ld 32x32b -> bias / activation / act-grad / residual -> 16B stores,
-// or red.global.add.v4.f32 for split-K weight-gradient accumulation).
+// fp32 accumulate in TMEM, 2 accumulator stages), warp2 = TMEM allocator, warps4-11 =
+// epilogue: pipelined tcgen05.ld 32x32b -> bias / erf-GELU (+ pre-activation side output) /
+// GELU'(aux) / residual (aux and residual tiles arrive by TMA) -> per-warp swizzled staging ->
+// TMA store; fp32 split-K weight gradients leave through TMA reduce-add
+// (cp.reduce.async.bulk.tensor .add).  Unaligned / fp32 outputs fall back to direct stores.
 #include "common.cuh"
 #include <cudaTypedefs.h>
 #include <stdlib.h>

@@ -55,10 +55,6 @@ __device__ __forceinline__ void mma_init(float* d, const uint32_t* a, const uint
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
-// 8x8 b16 transpose across the warp: turns a non-transposed ldmatrix fragment into the transposed one
-__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
-  uint32_t y; asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x)); return y;
-}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *(uint32_t*)&v;
