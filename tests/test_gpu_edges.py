@@ -161,3 +161,54 @@ def test_full_size_layernorm_statistics():
     xf = x.float()
     assert (mean - xf.mean(1)).abs().max().item() <= 1e-4
     assert (rstd - (xf.var(1, unbiased=False) + 1e-5).rsqrt()).abs().max().item() <= 1e-3 * rstd.max().item()
+
+
+def test_bias_gradient_fold_loses_no_update():
+    """Exactness probe for the atomics-free bias-gradient fold.  Q = K = 0 and a zero table make P uniform (1/392), dO
+    one-hot and integer V with zero sum per window make delta = 0 and dS_ij = v_j / 392, so every table slot's
+    gradient is (1/392) * (an integer sum of v_j over the pairs mapping to it).  One dropped or duplicated
+    read-modify-write shifts a slot by at least 1/392 = 2.6e-3; the tolerance is 4e-4."""
+    k = K()
+    grid, win, shift, cfg, heads, hd = (2, 8, 14, 14), (8, 7, 7), (0, 0, 0), (8, 7, 7), 2, 32
+    C = heads * hd
+    tokens = 2 * 8 * 14 * 14
+    g = torch.Generator().manual_seed(11)
+    v = torch.randint(1, 9, (tokens, heads), generator=g) * (torch.randint(0, 2, (tokens, heads), generator=g) * 2 - 1)
+    # make every window's values sum to zero per head (windows are 8 x 7 x 7 blocks of the [2,8,14,14] grid)
+    vv = v.view(2, 8, 2, 7, 2, 7, heads).float()
+    for b in range(2):
+        for ih in range(2):
+            for iw in range(2):
+                for h in range(heads):
+                    blk = vv[b, :, ih, :, iw, :, h]
+                    s = int(blk.sum().item())
+                    flat = blk.reshape(-1)
+                    i = 0
+                    while s != 0:                          # walk the sum to zero with +-1 steps, keeping 1 <= |v| <= 9
+                        step = -1 if s > 0 else 1
+                        if 1 <= abs(flat[i].item() + step) <= 9:
+                            flat[i] += step
+                            s += step
+                        i = (i + 1) % flat.numel()
+                    vv[b, :, ih, :, iw, :, h] = flat.view(8, 7, 7)
+    v = vv.reshape(tokens, heads)
+    assert (v.abs() >= 1).all()
+    qkv = torch.zeros(tokens, 3 * C)
+    do = torch.zeros(tokens, C)
+    for h in range(heads):
+        qkv[:, 2 * C + h * hd] = v[:, h]
+        do[:, h * hd] = 1.0
+    table = torch.zeros(15 * 13 * 13, heads)
+    sc = hd ** -0.5
+    o_r, lse_r = R.window_attn_fwd(qkv, table, grid, win, shift, cfg, heads, hd, sc)
+    dt_r = torch.zeros_like(table)
+    R.window_attn_bwd(qkv, o_r, do, lse_r, table, dt_r, grid, win, shift, cfg, heads, hd, sc)
+    assert o_r.abs().max().item() <= 1e-5                  # zero-sum windows: O = 0, delta = 0
+    q = qkv.cuda().bfloat16()
+    o, lse = k.window_attn_fwd(q, table.cuda(), grid, win, shift, cfg, heads, hd, sc)
+    dt = torch.zeros_like(table).cuda()
+    k.window_attn_bwd(q, o, do.cuda().bfloat16(), lse, table.cuda(), dt, grid, win, shift, cfg, heads, hd, sc)
+    torch.cuda.synchronize()
+    err = (dt.cpu() - dt_r).abs().max().item()
+    assert dt_r.abs().max().item() > 0.05
+    assert err <= 4e-4, (err, dt_r.abs().max().item())
