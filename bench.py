@@ -30,9 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TASK = "pt_contra%tva%tv%ta_caption%tva%tv%ta"
-# mean DRAM traffic of one tcgen05 GEMM launch of the C2 step, from profiles/launches_r1_final.txt
-# (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the 888 GEMM launches of one step: 117.82 GB)
-GEMM_DRAM_BYTES_PER_LAUNCH = 132.68e6
+# roofline.traffic is never a constant of this file: it is read from the ncu summary that tools/ncu_traffic.py writes
+# (profiles/gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, the
+# commit and command it was captured on) and reported only when that summary exists, else null.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "gemm_traffic.json")
 FLOPS_PER_SAMPLE = 1178.8e9  # fwd+bwd matmul FLOPs / sample at F8 A2 T32
 
 
@@ -74,6 +75,7 @@ def parse():
     ap.add_argument("--tokens", type=int, default=32)
     ap.add_argument("--geom", default="base", choices=["base", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-the-same-GPU competitor leg")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -85,6 +87,16 @@ def peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), d.get("hbm_gbs", 6650.0), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+def traffic_from_profile(args, B):
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+        if d.get("geom") == args.geom and d.get("batch") == B and d.get("frames") == args.frames:
+            return d["bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -129,7 +141,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 def cpu_step_fn(geom, B, F, A, T):
     import torch
-    from oracle import synth, valor_oracle as vo
+    from oracle import valor_oracle as vo
+    from tools import synth
     sd = synth.make_state_dict(geom, seed=0, include_buffers=False)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if not k.startswith("txt_encoder.") and k != "cls.decoder.weight"}
@@ -161,42 +174,121 @@ def cpu_step_fn(geom, B, F, A, T):
     return run
 
 
-def cpu_baseline(geom, F, A, T, steps=2, warmup=1, B=2):
+def cpu_baseline(geom, F, A, T, steps=2, warmup=1, B=2, budget_s=150.0):
+    """The reference's CPU PyTorch path (oracle port) on the box's host cores.  BASELINE.md §3.5 asks for all cores:
+    the step is first timed with every host thread and, because thousands of small ATen ops per step oversubscribe a
+    100+-thread OpenMP team, also with 32 threads; the FASTER of the two is the reported baseline and both are stated.
+    Steps stop early when `budget_s` of wall clock is used up; the number of steps actually run is returned."""
     import torch
-    # all host cores up to 32: the oracle issues thousands of small ATen ops per step and
-    # oversubscribes badly beyond that (a 200+-thread OpenMP team per op is slower, not faster)
-    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    ncpu = os.cpu_count() or 1
     run = cpu_step_fn(geom, B, F, A, T)
-    for _ in range(warmup):
-        run()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        losses = run()
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} full steps (fwd+bwd+clip+AdamW) of the oracle port at B={B} F={F} A={A} T={T} fp32, "
-                      f"{warmup} warm-up; {dt:.2f} s/step", "ms_per_step": dt * 1e3, "losses": losses}
+    trials = {}
+    t_start = time.perf_counter()
+    for threads in sorted({ncpu, min(ncpu, 32)}, reverse=True):
+        torch.set_num_threads(threads)
+        for _ in range(warmup):
+            run()
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            losses = run()
+            done += 1
+            if time.perf_counter() - t_start > budget_s * (1.0 if threads != ncpu else 0.5):
+                break
+        trials[threads] = ((time.perf_counter() - t0) / done, done)
+    best = min(trials, key=lambda k: trials[k][0])
+    dt, done = trials[best]
+    note = "; ".join(f"{k} threads: {v[0]:.2f} s/step over {v[1]} steps" for k, v in trials.items())
+    return {"value": B / dt, "unit": "samples/s", "cores": best, "kind": "port", "steps_run": done, "batch": B,
+            "host_cores": ncpu,
+            "sample": f"{done} full steps (fwd+bwd+clip+AdamW) of the oracle port at B={B} F={F} A={A} T={T} fp32, "
+                      f"{warmup} warm-up, on the GPU box's host ({ncpu} logical cores; {note}; fastest reported)",
+            "ms_per_step": dt * 1e3, "losses": losses}
+
+
+def gpu_eager_baseline(geom, B, F, A, T, dev, steps=3, warmup=2):
+    """The competitor SURVEY F10 / BASELINE.md §3.8 name: the reference's module math in stock torch eager on the SAME
+    B200 -- cuBLAS GEMMs + F.scaled_dot_product_attention, bf16 autocast over fp32 masters, torch's fused AdamW and
+    clip_grad_norm_ -- same synthetic batch and weights, B = the benchmarked per-GPU batch.  It runs the oracle's
+    restatement of the reference modules (the reference itself cannot travel to the GPU box); none of valor_b200's
+    kernels are involved."""
+    import torch
+    from oracle import valor_oracle as vo
+    from tools import synth
+    vo.USE_SDPA = True
+    try:
+        sd = synth.make_state_dict(geom, seed=0, include_buffers=False)
+        params = {k: v.to(dev).requires_grad_(True) for k, v in sd.items()
+                  if not k.startswith("txt_encoder.") and k != "cls.decoder.weight"}
+        full = dict(params)
+        for k in sd:
+            if k.startswith("txt_encoder."):
+                full[k] = params["multimodal_encoder." + k[len("txt_encoder."):]]
+        full["cls.decoder.weight"] = params["multimodal_encoder.embeddings.word_embeddings.weight"]
+        host = synth.make_batch(B, F, A, T, geom, seed=123)
+        ti, tl = synth.token_masker(host["txt_tokens"]["bert_tokens"], 0.6, seed=1234)
+        batch = {"video_pixels": host["video_pixels"].to(dev), "audio_spectrograms": host["audio_spectrograms"].to(dev),
+                 "txt_tokens": {"bert_tokens": host["txt_tokens"]["bert_tokens"].to(dev)}}
+        ti, tl = ti.to(dev), tl.to(dev)
+        decay = [p for k, p in params.items() if not vo.is_no_decay(k)]
+        no_decay = [p for k, p in params.items() if vo.is_no_decay(k)]
+        opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.01}, {"params": no_decay, "weight_decay": 0.0}],
+                                lr=1e-4, betas=(0.9, 0.98), eps=1e-6, fused=True)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                losses = vo.forward_pt(batch, full, geom, ti, tl, task=TASK)
+            opt.zero_grad(set_to_none=True)
+            sum(losses.values()).float().backward()
+            torch.nn.utils.clip_grad_norm_(list(params.values()), 5.0)
+            opt.step()
+            return losses
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            losses = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+        out = {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kind": "torch-eager port (cuBLAS + SDPA, "
+               "bf16 autocast, fused AdamW)", "batch": B, "steps_run": steps, "torch": torch.__version__,
+               "losses": {k: v.item() for k, v in losses.items()}, "peak_mem_gib": round(peak_gb, 1)}
+        del params, full, opt, batch
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        vo.USE_SDPA = False
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import synth
+    from tools import synth
     geom = synth.BASE if args.geom == "base" else synth.TINY
-    cb = cpu_baseline(geom, args.frames, args.clips, args.tokens, steps=max(1, min(args.steps, 3)),
-                      warmup=max(1, min(args.warmup, 1)))
+    # each "step" of this arm is one full training step of the same per-sample workload at B=2 (a bounded sample: B=32
+    # on host cores is ~100 s per step); the run is cut at ~150 s of wall clock and `steps` / `warmup` / `global_batch`
+    # below are what was actually EXECUTED, not what was asked for
+    cb = cpu_baseline(geom, args.frames, args.clips, args.tokens, steps=max(1, args.steps), warmup=1, budget_s=150.0)
     line = {"metric": "pretrain samples/sec (video+audio+text)", "value": cb["value"], "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "n_gpus": args.gpus, "steps": cb["steps_run"], "warmup": 1, "steps_requested": args.steps,
+            "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"VALOR-base (VideoSwin-B + AST + BERT-base fusion) pretrain step, per-GPU batch "
-                                   f"{args.batch}, {args.frames} frames 224^2, {args.clips} audio clips, {args.tokens} "
-                                   f"tokens (BASELINE configs[1])", "task": TASK, "global_batch": args.batch,
-                       "parallelism": "cpu", "dropout": "off (parity mode)", "geom": args.geom,
-                       "sample": f"each step = one full training step of the same per-sample workload at B=2 "
-                                 f"(samples/s is per-sample throughput; B={args.batch} would take minutes per step on CPU)"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "same_config": False,
+            "config": {"workload": f"VALOR-base (VideoSwin-B + AST + BERT-base fusion) pretrain step, {args.frames} frames "
+                                   f"224^2, {args.clips} audio clips, {args.tokens} tokens per sample (BASELINE configs[1] "
+                                   f"per-sample shape), executed at batch {cb['batch']} in fp32 on host cores",
+                       "task": TASK, "global_batch": cb["batch"], "parallelism": "cpu", "dropout": "off (parity mode)",
+                       "geom": args.geom,
+                       "sample": f"each step = one full training step at B={cb['batch']} (samples/s is per-sample "
+                                 f"throughput; the GPU arm's B={args.batch} would take ~100 s per step on host cores)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")},
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -211,7 +303,7 @@ def main():
         return main_reference(args)
     import torch
     import torch.distributed as dist
-    from valor_b200 import synthetic as synth   # seeded synthetic weights / batch (the GPU arm never touches oracle/)
+    from tools import synth   # seeded synthetic weights / batch (the GPU arm never touches oracle/)
     from valor_b200 import kernels as K
     from valor_b200.distributed import allreduce_grads
     from valor_b200.optim import get_lr_sched
@@ -318,8 +410,9 @@ def main():
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         return {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if args.geom == "base" and B == 32 else None,
-                "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's GEMM launches)",
+                "traffic": traffic_from_profile(args, B),
+                "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's GEMM "
+                                "launches; from profiles/gemm_traffic.json, null when no capture of this workload is committed)",
                 "peak_kind": f"{peak_kind} (sustained bf16)", "timing": "CUDA events inside a captured graph" if in_graph else
                 "CUDA events, eager launches", "launches_per_step": n_t, "gemm_ms_per_step": t_ms,
                 "gemm_tflop_per_step": fl / 1e12, "gemm_share_of_step": None}
@@ -445,10 +538,21 @@ def main():
         roof["gemm_share_of_step"] = roof["gemm_ms_per_step"] / ms_step
         line["roofline"] = roof
     log("roofline pass done")
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        try:
+            del graph
+            torch.cuda.empty_cache()
+            ge = gpu_eager_baseline(geom, B, F, A, T, dev)
+            ge["speedup_of_valor_b200"] = value / ge["value"]
+            line["gpu_eager_baseline"] = ge
+            log(f"torch-eager competitor on the same GPU: {ge['ms_per_step']:.1f} ms/step")
+        except Exception as ex:  # pragma: no cover
+            line["gpu_eager_baseline"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+            log(f"gpu eager baseline failed: {ex}")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline(geom, F, A, T, steps=2, warmup=1)
+        cb = cpu_baseline(geom, F, A, T, steps=2, warmup=1, budget_s=60.0)
         log("cpu baseline done")
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")}
     if rank == 0:
         emit(line)
     if world > 1:

@@ -147,7 +147,7 @@ def build_reference_valor(geom, state_dict, opts=None):
     (oracle.synth.Geometry) and load `state_dict` (reference key names) strictly for every
     key the reference owns.  Returns the nn.Module in train() mode semantics EXCEPT that
     stochastic layers are disabled (parity mode: Dropout p=0, DropPath off)."""
-    from oracle import synth
+    from tools import synth
     opts = opts or default_opts(audio_melbins=geom.audio_melbins, audio_target_length=geom.audio_frames,
                                 video_resolution=geom.resolution, contra_dim=geom.contra_dim)
     swin_sd = {k[len("video_encoder."):]: v for k, v in state_dict.items() if k.startswith("video_encoder.")}

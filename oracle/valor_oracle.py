@@ -84,16 +84,27 @@ def compute_mask(D, H, W, ws, ss):
     return am.masked_fill(am != 0, -100.0).masked_fill(am == 0, 0.0)
 
 
+# bench.py's "torch eager on the same B200" leg (the competitor SURVEY F10 names: cuBLAS + SDPA) flips this on; the
+# parity checker always runs the explicit matmul / softmax / matmul form of the reference.
+USE_SDPA = False
+
+
 def window_attention(x, sd, p, heads, rel_index, mask):
     """WindowAttention3D.forward, videoswin.py:137-163 (q scaled BEFORE q@k^T, :143)."""
     B_, N, C = x.shape
     qkv = linear(x, sd, p + "qkv").reshape(B_, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
     q = q * (C // heads) ** -0.5
-    attn = q @ k.transpose(-2, -1)
     table = sd[p + "relative_position_bias_table"]
     bias = table[rel_index[:N, :N].reshape(-1)].reshape(N, N, -1).permute(2, 0, 1).contiguous()
-    attn = attn + bias.unsqueeze(0)
+    if USE_SDPA:
+        am = bias.unsqueeze(0).to(q.dtype)
+        if mask is not None:
+            nW = mask.shape[0]
+            am = (am.unsqueeze(0) + mask.unsqueeze(1).unsqueeze(0).to(q.dtype)).expand(B_ // nW, nW, heads, N, N).reshape(-1, heads, N, N)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=am, scale=1.0)
+        return linear(o.transpose(1, 2).reshape(B_, N, C), sd, p + "proj")
+    attn = q @ k.transpose(-2, -1) + bias.unsqueeze(0)
     if mask is not None:
         nW = mask.shape[0]
         attn = attn.view(B_ // nW, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)
@@ -149,14 +160,14 @@ def patch_merging(x, sd, p):
 def swin_forward(video, sd, geom, p="video_encoder."):
     """SwinTransformer3D.forward, videoswin.py:441-458; PatchEmbed3D :361-376;
     BasicLayer.forward :329-345.  video: [B,3,D,H,W] -> [B, 8E, D, H/32, W/32]."""
-    from oracle.synth import relative_position_index
+    from tools.synth import relative_position_index
     x = F.pad(video, (0, 0, 0, 0, 0, 1))
     x = F.conv3d(x, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=(1, 4, 4))
     B, E, D, Wh, Ww = x.shape
     x = x.flatten(2).transpose(1, 2)
     x = layer_norm(x, sd[p + "patch_embed.norm.weight"], sd[p + "patch_embed.norm.bias"], 1e-5)
     x = x.transpose(1, 2).view(-1, E, D, Wh, Ww)
-    rel_index = relative_position_index(geom.swin_window)
+    rel_index = relative_position_index(geom.swin_window).to(video.device)
     window = geom.swin_window
     shift_full = tuple(i // 2 for i in window)
     for s, depth in enumerate(geom.swin_depths):
@@ -166,7 +177,7 @@ def swin_forward(video, sd, geom, p="video_encoder."):
         Dp = int(math.ceil(D / ws[0])) * ws[0]
         Hp = int(math.ceil(H / ws[1])) * ws[1]
         Wp = int(math.ceil(W / ws[2])) * ws[2]
-        mask = compute_mask(Dp, Hp, Wp, ws, ss)
+        mask = compute_mask(Dp, Hp, Wp, ws, ss).to(video.device)
         for b in range(depth):
             shift = (0, 0, 0) if b % 2 == 0 else shift_full
             x = swin_block(x, sd, f"{p}layers.{s}.blocks.{b}.", geom.swin_heads[s], window, shift, rel_index, mask)
@@ -205,6 +216,9 @@ def ast_mha(x, sd, p, heads):
     """MultiHeadAttention.forward, transformer.py:115-130 (no mask on the AST path)."""
     B, N, H = x.shape
     q, k, v = [linear(x, sd, f"{p}linears.{j}").view(B, -1, heads, H // heads).transpose(1, 2) for j in range(3)]
+    if USE_SDPA:
+        out = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).contiguous().view(B, -1, H)
+        return linear(out, sd, p + "linears.3")
     att = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.shape[-1])
     att = att.softmax(-1)
     out = torch.matmul(att, v).transpose(1, 2).contiguous().view(B, -1, H)
@@ -251,6 +265,10 @@ def bert_attention_core(q, k, v, heads, mask):
     def split(t):
         return t.view(t.shape[0], t.shape[1], heads, hd).permute(0, 2, 1, 3)
 
+    if USE_SDPA:
+        am = None if mask is None else mask.to(q.dtype).expand(B, heads, Tq, k.shape[1])
+        ctx = F.scaled_dot_product_attention(split(q), split(k), split(v), attn_mask=am)
+        return ctx.permute(0, 2, 1, 3).contiguous().view(B, Tq, H)
     s = torch.matmul(split(q), split(k).transpose(-1, -2)) / math.sqrt(hd)
     if mask is not None:
         s = s + mask
@@ -397,7 +415,7 @@ def forward_pt(batch, sd, geom, txt_input, txt_labels, task="pt_contra%tva%tv%ta
         wv = fine_weight(feat_v, sd, "video")
         wa = fine_weight(feat_a, sd, "audio")
         lo = []
-        ones = lambda f: torch.ones(*f.shape[:2], dtype=torch.long)
+        ones = lambda f: torch.ones(*f.shape[:2], dtype=torch.long, device=f.device)
         temp = sd["contra_temp"]
         # order of accumulation follows pretrain.py:397: (tva, tv, ta)
         if "tva" in contra_task:
@@ -424,8 +442,7 @@ def forward_pt(batch, sd, geom, txt_input, txt_labels, task="pt_contra%tva%tv%ta
                                audio_feat=audio_input if "a" in name else None, casual=True)
             out = out[:, : txt_input.shape[1], :][sel]
             scores = mlm_head(out, sd)
-            if name == "tva":
-                aux["caption_scores_tva"] = scores
+            aux[f"caption_scores_{name}"] = scores
             lo.append(F.cross_entropy(scores, txt_labels[sel]))
         losses["caption_loss"] = sum(lo) / len(lo)
     if return_aux:

@@ -173,7 +173,7 @@ def _window_rows(grid, win, shift):
 
 def _window_add(table, grid, win, shift, cfg_win, heads):
     from oracle import valor_oracle as vo
-    from oracle.synth import relative_position_index
+    from tools.synth import relative_position_index
     N = win[0] * win[1] * win[2]
     rpi = relative_position_index(cfg_win)[:N, :N]
     bias = table[rpi.reshape(-1)].reshape(N, N, heads).permute(2, 0, 1)  # [h,N,N]

@@ -86,7 +86,7 @@ def test_lr_schedule_and_param_groups_match_oracle():
 def test_token_masker_matches_seeded_restatement():
     """TokenMasker draws from Python `random` exactly like the reference (modeling.py:134-174)."""
     import random
-    from oracle import synth
+    from tools import synth
     from valor_b200.modeling import TokenMasker
     g = torch.Generator().manual_seed(7)
     tokens = torch.randint(1000, 20000, (4, 32), generator=g)

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--steps", type=int, default=2)
     args = ap.parse_args()
-    from valor_b200 import synthetic as synth
+    from tools import synth   # seeded synthetic weights / batch (the GPU arm never touches oracle/)
     from valor_b200.optim import get_lr_sched
     from valor_b200.pretrain import VALOR, default_opts
     import bench

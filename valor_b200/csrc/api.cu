@@ -83,11 +83,13 @@ int window_cta_bwd(const WindowIndex& ix, const void* qkv, long long ld, const v
 }  // namespace valor
 
 using namespace valor;
-// VALOR_WINDOW_FLASH=1 keeps window attention on the key-blocked flash kernels (A/B measurements)
 static bool window_use_cta(const WindowIndex& ix, int hd) {
+#ifdef VALOR_DEBUG   // -DVALOR_DEBUG only: VALOR_WINDOW_FLASH=1 keeps window attention on the key-blocked flash kernels (A/B)
   static int flash = -1;
   if (flash < 0) { const char* e = getenv("VALOR_WINDOW_FLASH"); flash = e ? atoi(e) : 0; }
-  return !flash && window_cta_eligible(ix, hd);
+  if (flash) return false;
+#endif
+  return window_cta_eligible(ix, hd);
 }
 #define ST ((cudaStream_t)stream)
 

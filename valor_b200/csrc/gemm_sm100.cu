@@ -630,8 +630,14 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
+  // release builds carry no result-changing switches; -DVALOR_DEBUG restores the diagnostic modes (bit 0: main loop
+  // only, bit 1: skip the stores) used for the round-1 pipeline measurements
+#ifdef VALOR_DEBUG
   static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("VALOR_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  if (dbg < 0) { const char* e = getenv("VALOR_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; if (dbg) fprintf(stderr, "valor_b200: VALOR_GEMM_DEBUG=%d active\n", dbg); }
+#else
+  const int dbg = 0;
+#endif
   kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, dbg, ep);
   return check_launch("gemm_sm100_kernel");
 }
@@ -727,8 +733,12 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   memset(&tc, 0, sizeof(tc));
   memset(&tp, 0, sizeof(tp));
   // fp32 accumulation (weight gradients) leaves through TMA reduce-add
+#ifdef VALOR_DEBUG
   static int no_acc_tma = -1;
   if (no_acc_tma < 0) { const char* e = getenv("VALOR_GEMM_NO_TMA_REDUCE"); no_acc_tma = e ? atoi(e) : 0; }
+#else
+  const int no_acc_tma = 0;
+#endif
   const bool acc_tma = ep.accumulate && ep.out_dtype == VALOR_DT_F32 && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0) &&
                        ep.bias == nullptr && ep.residual == nullptr && ep.act_aux == nullptr && ep.preact_out == nullptr &&
                        ep.act == VALOR_ACT_NONE && !a_kmajor && !b_kmajor && !no_acc_tma;

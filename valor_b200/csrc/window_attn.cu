@@ -873,9 +873,11 @@ int window_cta_bwd(const WindowIndex& ix, const void* qkv, long long ld, const v
   win_geometry(P, ix, H);
   P.qkv = (const bf16*)qkv; P.ld = ld; P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.scale = scale;
   P.dO = (const bf16*)dO; P.dqkv = (bf16*)dqkv; P.lddqkv = lddqkv; P.dtable = dtable;
-  static int no_dtab = -1;   // VALOR_WINDOW_NO_DTAB=1: skip the bias-table gradient (measurement of the fold's cost only)
-  if (no_dtab < 0) { const char* e = getenv("VALOR_WINDOW_NO_DTAB"); no_dtab = e ? atoi(e) : 0; }
+#ifdef VALOR_DEBUG   // -DVALOR_DEBUG only: VALOR_WINDOW_NO_DTAB=1 skips the bias-table gradient (cost measurement of the fold)
+  static int no_dtab = -1;
+  if (no_dtab < 0) { const char* e = getenv("VALOR_WINDOW_NO_DTAB"); no_dtab = e ? atoi(e) : 0; if (no_dtab) fprintf(stderr, "valor_b200: VALOR_WINDOW_NO_DTAB active\n"); }
   if (no_dtab) P.dtable = nullptr;
+#endif
   int n_dq = 0, n_dkv = 0;
   int gb = 0;
   VALOR_REQUIRE(bwd_warps(ix, P.NP, P.n_used, P.maxcode, n_dq, n_dkv, gb), "window_cta_bwd: window does not fit in shared memory");

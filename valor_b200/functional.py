@@ -465,5 +465,10 @@ class XentFn(Function):
     @staticmethod
     def backward(ctx, g):
         logits, labels, lse, acc = ctx.saved_tensors
+        # the gradient overwrites the saved logits in place (no second 187 MB tensor at the C2 size): a second
+        # backward through this node would read gradients as logits, so it is refused instead of being silently wrong
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("XentFn.backward ran twice (retain_graph): the logits buffer was already overwritten")
+        ctx.consumed = True
         g = g.contiguous().view(1).float()
         return K.xent_bwd(logits, labels, lse, acc, g), None

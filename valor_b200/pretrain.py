@@ -49,8 +49,43 @@ class VALOR(VALORModel):
     # ------------------------------------------------------------------------------------
     def forward(self, batch, task, compute_loss=True):
         if task.startswith("pt"):
+            if self.store is not None and self.training:
+                cache = self.__dict__.setdefault("_unused_cache", {})
+                if task not in cache:
+                    cache[task] = self.unused_parameter_names(task)
+                self.store.set_unused(cache[task])
             return self.forward_pt(batch, task, compute_loss=compute_loss)
         raise NotImplementedError("ret/cap/qa heads are the next §8 rows (SURVEY.md §8f N1-N3)")
+
+    def unused_parameter_names(self, task):
+        """Parameters that receive no gradient under `task` (the reference runs DDP with
+        find_unused_parameters=True for exactly these, train_utils.py:232; its AdamW skips them,
+        optim/adamw.py:52-53): the BERT pooler never runs, the prompt embedding is idle without task prompts
+        (bert.py:207-213), and a modality absent from every objective leaves its tower and heads untouched."""
+        used = "".join(x for t in task.split("_") for x in t.split("%")[1:])
+        contra = "".join(x for t in task.split("_") if "contra" in t for x in t.split("%")[1:])
+        caption = "".join(x for t in task.split("_") if "caption" in t for x in t.split("%")[1:])
+        dead = ["multimodal_encoder.pooler.", "multimodal_encoder.embeddings.prompt_embedding."]
+        if "v" not in used:
+            dead += ["video_encoder.", "hidden_trans_video_multimodal.", "video_frame_embedding", "video_type_embeddings"]
+        if "a" not in used:
+            dead += ["audio_encoder.", "audio_embeddings.", "hidden_trans_audio_multimodal.", "audio_frame_embedding",
+                     "audio_type_embeddings"]
+        if "v" not in contra:
+            dead += ["contra_head_v.", "video_fine_weight."]
+        if "a" not in contra:
+            dead += ["contra_head_a.", "audio_fine_weight."]
+        if not contra:
+            dead += ["contra_head_t.", "text_fine_weight.", "contra_temp"]
+        if "v" not in caption:
+            dead += ["hidden_trans_video_multimodal.", "video_frame_embedding", "video_type_embeddings"]
+        if "a" not in caption:
+            dead += ["audio_frame_embedding", "audio_type_embeddings"]
+        if not caption:
+            dead += ["cls.dense.", "cls.layernorm.", "cls.decoder.bias"]
+            dead += [f"multimodal_encoder.encoder.layer.{i}.cross_attn." for i in range(len(self.multimodal_encoder.encoder.layer))]
+        names = [n for n, _ in self.named_parameters()]
+        return sorted(n for n in names if any(n.startswith(d) or n == d for d in dead))
 
     def _fine_weight(self, feat, name):
         seq = getattr(self, f"{name}_fine_weight")
@@ -129,5 +164,7 @@ class VALOR(VALORModel):
             # labels == -1 rows are ignored.  Every pass shares the same labels, so the mean over all
             # npass*B*T rows equals the reference's mean of per-pass means (pretrain.py:473-479).
             labels = txt_labels.repeat_interleave(npass, 0).reshape(-1)
+            if getattr(self, "debug_capture", None) is not None:   # parity tests: the masked-token logits
+                self.debug_capture.update(logits=logits.detach().clone(), labels=labels, npass=npass, names=names)
             loss_dict["caption_loss"] = Fn.XentFn.apply(logits, labels).reshape(())
         return loss_dict
