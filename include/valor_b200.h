@@ -33,6 +33,7 @@ extern "C" {
 #define VALOR_BACKEND_AUTO 0
 #define VALOR_BACKEND_TENSOR 1 /* tcgen05 / TMEM / TMA (bf16 only) */
 #define VALOR_BACKEND_SIMT 2
+#define VALOR_BACKEND_MMA_SYNC 3 /* attention only: the round-1 mma.sync / ldmatrix kernels (kept as the A/B baseline) */
 
 const char* valor_last_error(void);
 int valor_version(void);
@@ -146,6 +147,10 @@ int valor_mean_pool_bwd(int dtype, const void* dy, void* dx, long long R, int X,
 int valor_colsum(int dtype, const void* dy, long long ld, float* db, long long M, int N, void* stream);
 /* dst[r,c] = cast(src[r,c]) over [R,C] with row pitches (flat: R=1) */
 int valor_cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, void* dst, long long dld, long long R, long long C, void* stream);
+/* x [R,C] fp32 (pitch xld) -> out [R,3C] bf16: two-term bf16 expansion x ~ hi + lo arranged [hi|hi|lo] (side 0) or
+ * [hi|lo|hi] (side 1), so one tcgen05 GEMM over K = 3C gives fp32-grade dot products of the L2-normalised contrastive
+ * features: torch.einsum('atd,bvd->abtv') of compute_fine_matrix_slice (pretrain.py:200) in the reference's fp32 */
+int valor_split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, void* stream);
 /* dh = dy * act'(h): gradient through GELU / QuickGELU / ReLU where it cannot ride a GEMM epilogue */
 int valor_act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, void* stream);
 int valor_strided_rows(int dtype, const void* src, long long sld, void* dst, long long dld, long long R, int C, int accumulate, void* stream);

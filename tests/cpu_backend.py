@@ -306,6 +306,12 @@ def colsum(dy, db):
     db += dy.float().sum(0)
 
 
+def split_bf16x3(x, side):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat((hi, hi, lo) if side == 0 else (hi, lo, hi), dim=1)
+
+
 def cast2d(src, dst):
     dst.copy_(src.to(dst.dtype))
 

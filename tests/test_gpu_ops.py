@@ -245,12 +245,16 @@ def test_mha(dtype, case):
     ((2, 4, 14, 14), (4, 7, 7), (0, 3, 3), 4),    # 196-token windows, masked border windows
     ((1, 8, 21, 14), (8, 7, 7), (0, 3, 3), 1),    # 392-token windows, 3x2 window grid, single head
 ])
-def test_window_attention(dtype, grid, win, shift, heads):
+@pytest.mark.parametrize("backend", ["auto", "mma_sync"])
+def test_window_attention(dtype, grid, win, shift, heads, backend):
     """shift / partition / relative-position bias / -100 mask evaluated in-kernel vs the reference's
     roll + window_partition + bias gather + compute_mask (videoswin.py:75-84,137-163,272-285).
     heads == 2 cases run head dim 64 (the key-blocked flash kernels), the others head dim 32
     (the one-CTA-per-window kernels)."""
     k = K()
+    if backend == "mma_sync" and dtype != torch.bfloat16:
+        pytest.skip("backend selection only matters for the bf16 tensor-core paths")
+    be = {"auto": k.BACKEND_AUTO, "mma_sync": k.BACKEND_MMA_SYNC}[backend]   # auto: tcgen05 kernels where eligible
     hd = 64 if (heads == 2 and grid[1] == 16) else 32
     C = heads * hd
     cfg_win = (8, 7, 7)
@@ -262,11 +266,12 @@ def test_window_attention(dtype, grid, win, shift, heads):
     o_r, lse_r = R.window_attn_fwd(qkv, table, grid, win, shift, cfg_win, heads, hd, scale)
     dt_r = torch.zeros_like(table)
     dqkv_r = R.window_attn_bwd(qkv, o_r, do, lse_r, table, dt_r, grid, win, shift, cfg_win, heads, hd, scale)
-    o, lse = k.window_attn_fwd(dev(qkv, dtype), dev(table), grid, win, shift, cfg_win, heads, hd, scale)
+    o, lse = k.window_attn_fwd(dev(qkv, dtype), dev(table), grid, win, shift, cfg_win, heads, hd, scale, backend=be)
     close(o, o_r, dtype, "window o")
+    close(lse.reshape(-1), lse_r.reshape(-1), torch.float32 if dtype == torch.float32 else dtype, "window lse")
     dt = torch.zeros_like(table).cuda()
     dqkv = k.window_attn_bwd(dev(qkv, dtype), o, dev(do, dtype), lse, dev(table), dt, grid, win, shift, cfg_win, heads,
-                             hd, scale)
+                             hd, scale, backend=be)
     close(dqkv, dqkv_r, dtype, "window dqkv")
     close(dt, dt_r, dtype, "window dtable")
 

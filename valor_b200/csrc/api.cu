@@ -59,6 +59,7 @@ int contrastive_bwd(const float*, const float*, const float*, const float*, cons
 int grad_sumsq(const float*, long long, float*, cudaStream_t);
 int clip_coef(const float*, float, float*, cudaStream_t);
 int adamw(float*, const float*, float*, float*, void*, long long, const float*, const float*, cudaStream_t);
+int split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, cudaStream_t st);
 bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
                        const void* k, const void* v, const void* o);
 int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
@@ -79,6 +80,14 @@ int window_cta_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O
 int window_cta_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
                    const float* lse, void* dqkv, long long lddqkv, float* dtable, int Pn, int H, int hd, float scale,
                    cudaStream_t st);
+
+bool window_sm100_fwd_eligible(const WindowIndex& ix, int hd);
+bool window_sm100_bwd_eligible(const WindowIndex& ix, int hd, bool want_dtab);
+int window_sm100_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
+                     const float* lse, void* dqkv, long long lddqkv, float* dtable, int Pn, int H, int hd, float scale,
+                     cudaStream_t st);
+int window_sm100_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
+                     int H, int hd, float scale, cudaStream_t st);
 
 }  // namespace valor
 
@@ -208,6 +217,8 @@ int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, lon
   const char* qb = (const char*)qkv;
   const bool ok = attn_mma_eligible(dtype, hd, ld, ld, ld, ldo, qb, qb + 2 * heads * hd, qb + 4 * heads * hd, O);
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_window_attn_fwd: tensor backend requested but not eligible");
+  if (backend != VALOR_BACKEND_SIMT && backend != VALOR_BACKEND_MMA_SYNC && ok && window_sm100_fwd_eligible(ix, hd))
+    return window_sm100_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);     // tcgen05 / TMEM
   if (backend != VALOR_BACKEND_SIMT && ok && window_use_cta(ix, hd))
     return window_cta_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
   if (backend != VALOR_BACKEND_SIMT && ok) return window_mma_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);
@@ -229,6 +240,10 @@ int valor_window_attn_bwd(int dtype, const void* qkv, long long ld, const void* 
   const int P = B * (D / wd) * (H / wh) * (W / ww);
   const int C = heads * hd;
   const long long tokens = (long long)B * D * H * W;
+  if (window_bwd_tensor_ok(dtype, hd, ld, backend) && backend != VALOR_BACKEND_MMA_SYNC && lddqkv % 8 == 0 && ldo % 8 == 0 &&
+      ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) &&
+      window_sm100_bwd_eligible(ix, hd, dtable != nullptr))
+    return window_sm100_bwd(ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);   // tcgen05 / TMEM
   if (window_bwd_tensor_ok(dtype, hd, ld, backend) && lddqkv % 8 == 0 && ldo % 8 == 0 &&
       ((((uintptr_t)qkv | (uintptr_t)O | (uintptr_t)dO | (uintptr_t)dqkv) & 15) == 0) && window_use_cta(ix, hd))
     return window_cta_bwd(ix, qkv, ld, O, dO, ldo, lse, dqkv, lddqkv, dtable, P, heads, hd, scale, ST);
@@ -281,6 +296,9 @@ int valor_colsum(int dtype, const void* dy, long long ld, float* db, long long M
 }
 int valor_cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, void* dst, long long dld, long long R, long long C, void* stream) {
   return cast2d(src_dtype, dst_dtype, src, sld, dst, dld, R, C, ST);
+}
+int valor_split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, void* stream) {
+  return split_bf16x3(x, xld, out, R, C, side, ST);
 }
 int valor_act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, void* stream) {
   return act_bwd(dtype, dy, h, dh, n, act, ST);

@@ -423,6 +423,31 @@ int cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, void* d
   return check_launch("cast2d_kernel");
 }
 
+// x [R, C] fp32 -> out [R, 3C] bf16 holding the two-term bf16 expansion x ~ hi + lo (|x - hi - lo| <= 2^-17 |x|) laid out
+// so that ONE bf16 tensor-core GEMM with K = 3C evaluates  hi.hi' + hi.lo' + lo.hi'  (fp32-grade dot products: the
+// fine-grained contrastive similarity of L2-normalised features, pretrain.py:200, would otherwise lose 2^-9 per operand):
+//   side 0 (left operand):  [hi | hi | lo]        side 1 (right operand):  [hi | lo | hi]
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, long long xld, bf16* __restrict__ out, long long C, long long R, int side) {
+  const long long n = R * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C, c = i - r * C;
+    const float v = x[r * xld + c];
+    const bf16 hi = __float2bfloat16_rn(v);
+    const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    bf16* o = out + r * 3 * C + c;
+    o[0] = hi;
+    o[C] = side == 0 ? hi : lo;
+    o[2 * C] = side == 0 ? lo : hi;
+  }
+}
+int split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, cudaStream_t st) {
+  if (R * C == 0) return 0;
+  long long g = (R * C + 255) / 256;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  split_bf16x3_kernel<<<(unsigned)g, 256, 0, st>>>(x, xld, (bf16*)out, C, R, side);
+  return check_launch("split_bf16x3_kernel");
+}
+
 // dh = dy * act'(h)   (flat, same dtype)
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, T* __restrict__ dh, long long n, int act) {

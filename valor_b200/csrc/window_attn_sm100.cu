@@ -1,0 +1,905 @@
+// valor_b200 — VideoSwin shifted-window attention on tcgen05 / TMEM (sm_100a), one CTA per (window, head).
+//
+// Reference math: WindowAttention3D.forward (videoswin.py:137-163) + roll / window_partition / compute_mask
+// (videoswin.py:75-84,191-226,272-285), evaluated on the natural token order like window_attn.cu (same index tables).
+//
+// Forward, per 128-query tile of the window (N <= 512 tokens, head dim 32):
+//   S[128, N]  = Q_tile . K^T          tcgen05.mma, operands gathered into 64-byte-swizzled shared tiles (K-major),
+//                                       fp32 accumulator in tensor memory (N columns)
+//   pass A     : one query row per thread (tcgen05.ld 32x32b): v = S*scale*log2e + bias2[code_q - code_k] (+ mask),
+//                row maximum, v written back to tensor memory (tcgen05.st)
+//   pass B     : p = exp2(v - max), row sum, bf16 P written once into 128-byte-swizzled 64-key panels
+//   O[128, 32] = P . V                  tcgen05.mma per panel as soon as it is written (A = panel, K-major;
+//                                       B = V rows as stored, MN-major), accumulator double-buffered in tensor memory
+// Eight "element" warps (two per tensor-memory lane quarter, interleaved 64-key panels) do the softmax; one thread
+// issues every MMA; completion travels through mbarriers (tcgen05.commit).  No mma.sync / ldmatrix anywhere.
+#include "common.cuh"
+#include "attention.cuh"
+#include <algorithm>
+
+namespace valor {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int HD = 32;          // head dim (all VideoSwin stages)
+constexpr int ROWB = HD * 2;    // bytes per token row of a Q/K/V tile
+
+// ---- PTX ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n)); }
+__device__ __forceinline__ void bar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t a = s_u32(b);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* b) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(b)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+#define VALOR_TMEM_LD32(taddr, v)                                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"                                                                  \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"                                   \
+               " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),   \
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
+               : "r"(taddr))
+#define VALOR_TMEM_ST32(taddr, v)                                                                                       \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0],"                                                            \
+               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"                                  \
+               " %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"                        \
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),     \
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),           \
+                 "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),         \
+                 "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory")
+#define VALOR_TMEM_LD16(taddr, v)                                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"                                                                  \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                           \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])    \
+               : "r"(taddr))
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *(uint32_t*)&v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+// instruction descriptor: fp32 accumulate, bf16 x bf16, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+}
+// 64-byte token rows: 16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3)  == the SWIZZLE_64B pattern (tile base 512-aligned)
+__device__ __forceinline__ uint32_t tile64(int row, int chunk) { return (uint32_t)(row * ROWB + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ int sdiv(int i, int inv) { return (int)(((unsigned)i * (unsigned)inv) >> 20); }
+__host__ __device__ __forceinline__ int sinv(int d) { return (int)(((1u << 20) + d - 1) / d); }
+
+struct FwdParams {
+  const bf16* qkv; long long ld;
+  bf16* O; long long ldo;
+  float* lse;
+  float scale2;                    // scale * log2(e)
+  int heads;
+  int nqt;                         // 128-query tiles
+  int NPK;                         // keys rounded up to 16
+  int np;                          // 64-key panels
+  int n_used, maxcode, center;
+  WindowIndex win;
+};
+
+struct FwdSmem {
+  unsigned char *Qs, *Ks, *Vs, *Pp;
+  int* qrow; uint32_t *qcode, *kcode, *qreg;
+  float* tab2;          // bias slice * log2e
+  float* xch;           // [2 tile parities][2 stats: max, sum][2 halves][128 rows]
+  uint64_t* bars;       // s_full, s_free, o_full[2], p_full[8]
+  uint32_t* tmem_slot;
+};
+
+static inline size_t fwd_smem_bytes(int nqt, int NPK, int np, int n_used) {
+  size_t b = 1024;                                   // alignment slack
+  b += (size_t)nqt * 128 * ROWB;                     // Q
+  b += 2 * (((size_t)NPK * ROWB + 1023) / 1024 * 1024);   // K, V
+  b += (size_t)np * 16384;                           // P panels
+  b += (size_t)4 * 512 * 4;                          // qrow qcode kcode qreg (512 entries each)
+  b += ((size_t)n_used * 4 + 15) / 16 * 16;
+  b += 2 * 2 * 2 * 128 * 4;
+  b += 16 * 8 + 16;
+  return b;
+}
+
+__device__ __forceinline__ FwdSmem fwd_carve(unsigned char* raw, const FwdParams& P) {
+  unsigned char* base = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  FwdSmem S;
+  S.Qs = base;
+  const size_t kvb = ((size_t)P.NPK * ROWB + 1023) / 1024 * 1024;
+  S.Ks = S.Qs + (size_t)P.nqt * 128 * ROWB;
+  S.Vs = S.Ks + kvb;
+  S.Pp = S.Vs + kvb;
+  S.qrow = (int*)(S.Pp + (size_t)P.np * 16384);
+  S.qcode = (uint32_t*)(S.qrow + 512);
+  S.kcode = S.qcode + 512;
+  S.qreg = S.kcode + 512;
+  S.tab2 = (float*)(S.qreg + 512);
+  S.xch = (float*)((unsigned char*)S.tab2 + ((size_t)P.n_used * 4 + 15) / 16 * 16);
+  S.bars = (uint64_t*)(S.xch + 2 * 2 * 2 * 128);
+  S.tmem_slot = (uint32_t*)(S.bars + 16);
+  return S;
+}
+
+// Per-token words (same conventions as window_attn.cu): qcode = 4*(code + maxcode), kcode = 4*code (byte offsets into
+// the bias slice: slot of a pair = qcode - kcode), qreg = compute_mask region id, qrow = global token row (-1: padding).
+__device__ __forceinline__ bool build_tables(const WindowIndex& ix, int maxcode, int center, int n_used, int p, int h, int* qrow,
+                                             uint32_t* qcode, uint32_t* kcode, uint32_t* qreg, float* tab2, int entries) {
+  const int nWw = ix.W / ix.ww, nWh = ix.H / ix.wh, nWd = ix.D / ix.wd;
+  int tq = p;
+  const int iw = tq % nWw; tq /= nWw;
+  const int ih = tq % nWh; tq /= nWh;
+  const int id = tq % nWd;
+  const int b = tq / nWd;
+  const int od = id * ix.wd, oh = ih * ix.wh, ow = iw * ix.ww;
+  const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
+  const int hw = ix.wh * ix.ww;
+  const int inv_hw = sinv(hw), inv_ww = sinv(ix.ww);
+  const bool masked = (ix.sd > 0 && id == nWd - 1) || (ix.sh > 0 && ih == nWh - 1) || (ix.sw > 0 && iw == nWw - 1);
+  for (int i = threadIdx.x; i < entries; i += blockDim.x) {
+    if (i < ix.N) {
+      const int ld = sdiv(i, inv_hw);
+      const int rem = i - ld * hw;
+      const int lh = sdiv(rem, inv_ww);
+      const int lw = rem - lh * ix.ww;
+      const int cd = od + ld, ch = oh + lh, cw = ow + lw;
+      int d = cd + ix.sd; if (d >= ix.D) d -= ix.D;     // shifted[c] = x[(c + shift) mod size]  (videoswin.py:206)
+      int hh = ch + ix.sh; if (hh >= ix.H) hh -= ix.H;
+      int w = cw + ix.sw; if (w >= ix.W) w -= ix.W;
+      uint32_t reg = 0;
+      if (masked) reg = (uint32_t)(ix.region(cd, ix.D, ix.wd, ix.sd) * 9 + ix.region(ch, ix.H, ix.wh, ix.sh) * 3 + ix.region(cw, ix.W, ix.ww, ix.sw));
+      const int code = ld * cH + lh * cW + lw;
+      qrow[i] = ((b * ix.D + d) * ix.H + hh) * ix.W + w;
+      qcode[i] = (uint32_t)(4 * (code + maxcode));
+      kcode[i] = (uint32_t)(4 * code);
+      qreg[i] = reg;
+    } else {
+      qrow[i] = -1; qcode[i] = (uint32_t)(4 * maxcode); kcode[i] = 0u; qreg[i] = 0u;
+    }
+  }
+  const float* src = ix.table + (size_t)(center - maxcode) * ix.heads + h;
+  for (int r = threadIdx.x; r < n_used; r += blockDim.x) tab2[r] = src[(size_t)r * ix.heads] * kLog2e;
+  return masked;
+}
+
+__device__ __forceinline__ void gather_rows(unsigned char* dst, const bf16* src, long long ld, int col0, const int* rows, int nrows) {
+  const uint32_t d0 = s_u32(dst);
+  for (int c = threadIdx.x; c < nrows * 4; c += blockDim.x) {
+    const int r = c >> 2, ch = c & 3;
+    const int gr = rows[r];
+    cp_async16(d0 + tile64(r, ch), src + (size_t)(gr < 0 ? 0 : gr) * ld + col0 + ch * 8, gr < 0 ? 0 : 16);
+  }
+}
+
+// Candidates for the descriptor fields the probe (tools/probe) settles; compile-time so the kernel carries no switches.
+#ifndef VALOR_SW64_K_LBO
+#define VALOR_SW64_K_LBO 0
+#endif
+#ifndef VALOR_SW64_MN_LBO
+#define VALOR_SW64_MN_LBO 0
+#endif
+
+constexpr int TMEM_S = 0;        // S columns [0, NPK)
+constexpr int TMEM_O = 448;      // O accumulators: 448..479, 480..511
+
+template <bool MASKED>
+__device__ __forceinline__ void fwd_element_warps(const FwdParams& P, const FwdSmem& S, int p, int h, uint32_t tmem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = warp - 4;
+  const int qtr = e & 3, half = e >> 2;           // tensor-memory lane quarter (hardware: warp % 4), panel parity
+  const int N = P.win.N;
+  const uint32_t lane_t = tmem + ((uint32_t)(qtr * 32) << 16);
+  uint64_t* s_full = S.bars; uint64_t* s_free = S.bars + 1; uint64_t* o_full = S.bars + 2; uint64_t* p_full = S.bars + 4;
+  const uint32_t tab_s = s_u32(S.tab2), kc_s = s_u32(S.kcode), kr_s = s_u32(S.qreg);
+  const int rloc = qtr * 32 + lane;               // row inside the 128-query tile
+  float m_prev = 0.f, l_prev = 0.f;
+  const float kMask2 = -100.0f * kLog2e;          // videoswin.py:284
+  for (int qt = 0; qt <= P.nqt; ++qt) {
+    float m_row = -INFINITY, l_row = 0.f;
+    const int q = qt * 128 + rloc;
+    const bool warp_live = qt < P.nqt && (qt * 128 + qtr * 32) < N;
+    if (qt < P.nqt) {
+      bar_wait(s_full, qt & 1);
+      tc_fence_after();
+      if (warp_live) {
+        // ---------------- pass A: logits (log2 units) + row maximum, written back to tensor memory
+        const uint32_t qaddr = tab_s + S.qcode[min(q, 511)];
+        const uint32_t qrg = S.qreg[min(q, 511)];
+        for (int pn = half; pn < P.np; pn += 2) {
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub) {
+            const int c0 = pn * 64 + sub * 32;
+            if (c0 >= P.NPK) break;
+            uint32_t v[32];
+            VALOR_TMEM_LD32(lane_t + TMEM_S + c0, v);
+            uint32_t kc[32], kr[32];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint4 t = lds_v4(kc_s + (c0 + g * 4) * 4);
+              kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
+              if (MASKED) {
+                const uint4 u = lds_v4(kr_s + (c0 + g * 4) * 4);
+                kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
+              }
+            }
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = fmaf(__uint_as_float(v[j]), P.scale2, lds_f32(qaddr - kc[j]));
+              if (MASKED && qrg != kr[j]) x += kMask2;
+              if (c0 + j >= N) x = -INFINITY;           // padding key (warp-uniform)
+              m_row = fmaxf(m_row, x);
+              v[j] = __float_as_uint(x);
+            }
+            VALOR_TMEM_ST32(lane_t + TMEM_S + c0, v);
+          }
+        }
+        tmem_wait_st();
+        S.xch[(((qt & 1) * 2 + 0) * 2 + half) * 128 + rloc] = m_row;
+      }
+      named_bar(1 + qtr, 64);                             // the two warps of this lane quarter exchange their maxima
+      if (warp_live) m_row = fmaxf(m_row, S.xch[(((qt & 1) * 2 + 0) * 2 + (half ^ 1)) * 128 + rloc]);
+    }
+    // ---------------- epilogue of the previous tile (its P.V is complete: the panels are free again)
+    if (qt > 0) {
+      const int pt = qt - 1;
+      if (qt == P.nqt) named_bar(1 + qtr, 64);            // (earlier tiles: the maximum exchange above already ordered the row sums)
+      bar_wait(&o_full[pt & 1], (pt >> 1) & 1);
+      tc_fence_after();
+      const int qp = pt * 128 + rloc;
+      if ((pt * 128 + qtr * 32) < N) {
+        uint32_t o[16];
+        VALOR_TMEM_LD16(lane_t + TMEM_O + (pt & 1) * 32 + half * 16, o);
+        const float l_tot = l_prev + S.xch[(((pt & 1) * 2 + 1) * 2 + (half ^ 1)) * 128 + rloc];
+        tmem_wait_ld();
+        if (qp < N) {
+          const float inv = 1.0f / l_tot;
+          bf16* dst = P.O + (size_t)S.qrow[qp] * P.ldo + h * HD + half * 16;
+          uint4 w0, w1;
+          w0.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          w0.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          w0.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          w0.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          w1.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+          w1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+          w1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+          w1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+          *(uint4*)dst = w0;
+          *(uint4*)(dst + 8) = w1;
+          if (half == 0) P.lse[((size_t)p * P.heads + h) * N + qp] = (m_prev + log2f(l_tot)) * kLn2;
+        }
+      }
+      tc_fence_before();
+    }
+    if (qt == P.nqt) break;
+    // ---------------- pass B: probabilities, row sum, bf16 panels
+    for (int pn = half; pn < P.np; pn += 2) {
+      if (warp_live) {
+        const uint32_t prow = s_u32(S.Pp) + pn * 16384 + rloc * 128;
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c0 = pn * 64 + sub * 32;
+          if (c0 >= P.NPK) break;
+          uint32_t v[32];
+          VALOR_TMEM_LD32(lane_t + TMEM_S + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              pv[j] = ex2f(__uint_as_float(v[g * 8 + j]) - m_row);
+              l_row += pv[j];
+            }
+            const int ch = sub * 4 + g;
+            const uint32_t a = prow + (uint32_t)((ch ^ (rloc & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pack_bf16(pv[0], pv[1])), "r"(pack_bf16(pv[2], pv[3])),
+                         "r"(pack_bf16(pv[4], pv[5])), "r"(pack_bf16(pv[6], pv[7])) : "memory");
+          }
+        }
+      }
+      proxy_fence();                                      // generic-proxy panel writes -> visible to the MMA unit
+      __syncwarp();
+      if (lane == 0) bar_arrive(&p_full[pn]);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) bar_arrive(s_free);
+    if (warp_live) S.xch[(((qt & 1) * 2 + 1) * 2 + half) * 128 + rloc] = l_row;
+    m_prev = m_row; l_prev = l_row;
+  }
+}
+
+__global__ void __launch_bounds__(384, 1)
+window_fwd_sm100_kernel(FwdParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const FwdSmem S = fwd_carve(smem_raw, P);
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = P.heads * HD, col0 = h * HD;
+  uint64_t* s_full = S.bars; uint64_t* s_free = S.bars + 1; uint64_t* o_full = S.bars + 2; uint64_t* p_full = S.bars + 4;
+  if (threadIdx.x == 0) {
+    bar_init(s_full, 1); bar_init(s_free, 8); bar_init(&o_full[0], 1); bar_init(&o_full[1], 1);
+    for (int i = 0; i < 8; ++i) bar_init(&p_full[i], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(S.tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  const bool masked = build_tables(P.win, P.maxcode, P.center, P.n_used, p, h, S.qrow, S.qcode, S.kcode, S.qreg, S.tab2, 512);
+  __syncthreads();
+  gather_rows(S.Qs, P.qkv, P.ld, col0, S.qrow, P.nqt * 128);
+  gather_rows(S.Ks, P.qkv + C, P.ld, col0, S.qrow, P.NPK);
+  gather_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.qrow, P.NPK);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *S.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t Qs = s_u32(S.Qs), Ks = s_u32(S.Ks), Vs = s_u32(S.Vs), Pp = s_u32(S.Pp);
+      int n0 = P.NPK, n1 = 0;
+      if (P.NPK > 256) { n0 = ((P.NPK / 2 + 15) / 16) * 16; n1 = P.NPK - n0; }
+      const uint32_t id_s0 = make_idesc(n0, 0, 0), id_s1 = make_idesc(n1 > 0 ? n1 : 16, 0, 0), id_pv = make_idesc(HD, 0, 1);
+      for (int qt = 0; qt < P.nqt; ++qt) {
+        if (qt > 0) { bar_wait(s_free, (qt - 1) & 1); tc_fence_after(); }
+        // S = Q_tile . K^T : two 16-deep k-steps over the 32 channels
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t ad = smem_desc(Qs + qt * 128 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4);
+          tc_mma(tmem + TMEM_S, ad, smem_desc(Ks + k * 32, VALOR_SW64_K_LBO, 512, 4), id_s0, k);
+          if (n1 > 0) tc_mma(tmem + TMEM_S + n0, ad, smem_desc(Ks + n0 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4), id_s1, k);
+        }
+        tc_commit(s_full);
+        // O = P . V : panel by panel as the element warps publish them
+        const uint32_t tO = tmem + TMEM_O + (qt & 1) * 32;
+        for (int pn = 0; pn < P.np; ++pn) {
+          bar_wait(&p_full[pn], qt & 1);
+          tc_fence_after();
+          const int ksteps = min(4, (P.NPK - pn * 64) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            tc_mma(tO, smem_desc(Pp + pn * 16384 + k * 32, 0, 1024, 2),
+                   smem_desc(Vs + (pn * 64 + k * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4), id_pv, (pn | k) ? 1u : 0u);
+        }
+        tc_commit(&o_full[qt & 1]);
+      }
+    }
+  } else if (warp >= 4) {
+    if (masked) fwd_element_warps<true>(P, S, p, h, tmem);
+    else fwd_element_warps<false>(P, S, p, h, tmem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+
+// ==========================================================================================
+// backward
+// ==========================================================================================
+// Block (kt, qt) = 128 keys x 128 queries of the window; k-tiles outer, q-tiles inner.  Tensor memory (512 columns):
+//   [0,128)   S   = Q_qt . K_kt^T      two 64-key halves, each handed to the element warps on its own barrier
+//   [128,256) dP  = dO_qt . V_kt^T
+//   [256,384) dQ_qt accumulators (4 x 32 columns), live across the k-tiles
+//   [384,512) dK | dV accumulators of the current k-tile, double-buffered (2 x (32 + 32))
+// Element warps (one query row per thread): p = exp2(s*scale2 + bias2 - lse2), ds = p * (dP - delta); bf16 P and dS go
+// ONCE into 128-byte-swizzled [query][key] panels that serve  dV += P^T.dO  and  dK += dS^T.Q  as MN-major A operands and
+// dQ += dS.K as a K-major A operand; fp32 ds is folded into the warp's private slice of the bias-table gradient
+// (plain load / add / store: inside one key column the 32 queries of a warp hit distinct slots and a warp's shared-memory
+// instructions retire in order), the slices are merged per k-tile into a CTA table and sent to global memory once.
+struct BwdParams {
+  const bf16* qkv; long long ld;
+  const bf16* O; const bf16* dO; long long ldo;
+  const float* lse;
+  bf16* dqkv; long long lddqkv;
+  float* dtable;
+  float scale, scale2;
+  int heads;
+  int nqt, nkt;
+  int n_used, maxcode, center;
+  int gt_bytes;                    // bytes of one element warp's private gradient slice
+  WindowIndex win;
+};
+
+struct BwdSmem {
+  unsigned char *Qs, *dOs, *Ks, *Vs, *Pb, *dSb;
+  int* qrow; uint32_t *qcode, *kcode, *qreg;
+  float* tab2;
+  float* ld2;           // [512][2]: lse * log2e (+inf on padding rows), -delta
+  float* ctab;          // CTA-level bias-table gradient [n_used]
+  unsigned char* gpriv; // 8 private slices
+  uint64_t* bars;
+  uint32_t* tmem_slot;
+};
+
+static inline size_t bwd_smem_bytes(int nqt, int n_used, int gt_bytes, bool want_dtab) {
+  size_t b = 1024;
+  b += (size_t)2 * nqt * 128 * ROWB;       // Q, dO
+  b += 2 * 128 * ROWB;                     // K, V tile
+  b += 2 * 32768;                          // P, dS panels
+  b += (size_t)4 * 512 * 4;
+  const size_t tabb = ((size_t)n_used * 4 + 15) / 16 * 16;
+  b += tabb;
+  b += 512 * 2 * 4;
+  if (want_dtab) b += tabb + (size_t)8 * gt_bytes;
+  b += 16 * 8 + 16;
+  return b;
+}
+
+__device__ __forceinline__ BwdSmem bwd_carve(unsigned char* raw, const BwdParams& P) {
+  unsigned char* base = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  BwdSmem S;
+  const size_t qb = (size_t)P.nqt * 128 * ROWB;
+  S.Qs = base;
+  S.dOs = S.Qs + qb;
+  S.Ks = S.dOs + qb;
+  S.Vs = S.Ks + 128 * ROWB;
+  S.Pb = S.Vs + 128 * ROWB;
+  S.dSb = S.Pb + 32768;
+  S.qrow = (int*)(S.dSb + 32768);
+  S.qcode = (uint32_t*)(S.qrow + 512);
+  S.kcode = S.qcode + 512;
+  S.qreg = S.kcode + 512;
+  S.tab2 = (float*)(S.qreg + 512);
+  const size_t tabb = ((size_t)P.n_used * 4 + 15) / 16 * 16;
+  S.ld2 = (float*)((unsigned char*)S.tab2 + tabb);
+  unsigned char* nxt = (unsigned char*)(S.ld2 + 1024);
+  S.ctab = (float*)nxt;
+  S.gpriv = nxt + tabb;
+  if (P.dtable != nullptr) nxt = S.gpriv + (size_t)8 * P.gt_bytes;
+  S.bars = (uint64_t*)nxt;
+  S.tmem_slot = (uint32_t*)(S.bars + 16);
+  return S;
+}
+
+constexpr int TB_S = 0, TB_DP = 128, TB_DQ = 256, TB_DKV = 384;
+__device__ __forceinline__ float ldv_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void stv_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+
+// barrier slots
+enum { B_SFULL = 0, B_SFREE = 2, B_PDFULL = 4, B_PDFREE = 5, B_KVFULL = 6, B_KVLOAD = 8, B_QFULL = 9 };
+
+template <bool MASKED>
+__device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdSmem& S, int h, uint32_t tmem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = warp - 4;
+  const int qtr = e & 3, half = e >> 2;
+  const int et = threadIdx.x - 128;                 // 0..255 among the element threads
+  const int N = P.win.N;
+  const int C = P.heads * HD;
+  const uint32_t lane_t = tmem + ((uint32_t)(qtr * 32) << 16);
+  uint64_t* bars = S.bars;
+  const uint32_t tab_s = s_u32(S.tab2), kc_s = s_u32(S.kcode), kr_s = s_u32(S.qreg);
+  const int rloc = qtr * 32 + lane;
+  const bool want_dtab = P.dtable != nullptr;
+  const uint32_t gt_s = s_u32(S.gpriv) + (uint32_t)(e * P.gt_bytes);
+  const float kMask2 = -100.0f * kLog2e;
+  const uint32_t pb_s = s_u32(S.Pb) + half * 16384 + rloc * 128, dsb_s = s_u32(S.dSb) + half * 16384 + rloc * 128;
+  const int sw = rloc & 7;
+  for (int kt = 0; kt < P.nkt; ++kt) {
+    // key range of this warp's column half: codes grow with the token index
+    const int k_first = kt * 128 + half * 64;
+    const int k_last = min(k_first + 63, N - 1);
+    const bool has_keys = k_first < N;
+    const int kc_hi = has_keys ? (int)S.kcode[k_last] : 0;
+    const int lo_b = 4 * P.maxcode - kc_hi;           // smallest slot byte offset this warp can touch in this k-tile
+    for (int qt = 0; qt < P.nqt; ++qt) {
+      const int b = kt * P.nqt + qt;
+      const int q = qt * 128 + rloc;
+      const bool live = has_keys && (qt * 128 + qtr * 32) < N;
+      const uint32_t qcode = S.qcode[q];
+      const uint32_t qaddr = tab_s + qcode;
+      const uint32_t gaddr = gt_s + qcode - (uint32_t)lo_b;
+      const uint32_t qrg = S.qreg[q];
+      const float l2 = S.ld2[2 * q], nd = S.ld2[2 * q + 1];
+      bar_wait(&bars[B_SFULL + half], b & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {
+        const int c0 = half * 64 + sub * 16;
+        const int kg = kt * 128 + c0;
+        uint32_t pw[8], dw[8];
+        if (live && kg < N) {
+          uint32_t sv[16], dv[16];
+          VALOR_TMEM_LD16(lane_t + TB_S + c0, sv);
+          VALOR_TMEM_LD16(lane_t + TB_DP + c0, dv);
+          uint32_t kc[16], kr[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 t = lds_v4(kc_s + (kg + g * 4) * 4);
+            kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
+            if (MASKED) {
+              const uint4 u = lds_v4(kr_s + (kg + g * 4) * 4);
+              kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
+            }
+          }
+          tmem_wait_ld();
+          if (sub == 3) {   // every tensor-memory read of this block's half is in registers: hand S / dP back to the MMAs
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
+          }
+          float pf[16], df[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = fmaf(__uint_as_float(sv[j]), P.scale2, lds_f32(qaddr - kc[j]));
+            if (MASKED && qrg != kr[j]) x += kMask2;
+            float pr = ex2f(x - l2);                   // l2 = +inf on padding queries -> 0
+            if (kg + j >= N) pr = 0.f;                 // padding key (warp-uniform)
+            pf[j] = pr;
+            df[j] = pr * (__uint_as_float(dv[j]) + nd);
+          }
+          if (want_dtab) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (kg + j < N) {
+                const uint32_t slot = gaddr - kc[j];
+                stv_f32(slot, ldv_f32(slot) + df[j]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]); dw[j] = pack_bf16(df[2 * j], df[2 * j + 1]); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pw[j] = dw[j] = 0u;
+          if (sub == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
+          }
+        }
+        if (sub == 0 && b > 0) bar_wait(&bars[B_PDFREE], (b - 1) & 1);   // the previous block's dV / dK / dQ MMAs have read the panels
+        const uint32_t o0 = (uint32_t)(((sub * 2) ^ sw) << 4), o1 = (uint32_t)(((sub * 2 + 1) ^ sw) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o0), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o1), "r"(pw[4]), "r"(pw[5]), "r"(pw[6]), "r"(pw[7]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o0), "r"(dw[0]), "r"(dw[1]), "r"(dw[2]), "r"(dw[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o1), "r"(dw[4]), "r"(dw[5]), "r"(dw[6]), "r"(dw[7]) : "memory");
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) bar_arrive(&bars[B_PDFULL]);
+    }
+    // ---------------- k-tile epilogue: dK (half 0 warps) / dV (half 1 warps) rows of this tile
+    bar_wait(&bars[B_KVFULL + (kt & 1)], (kt >> 1) & 1);
+    tc_fence_after();
+    {
+      const int key = kt * 128 + rloc;
+      if (kt * 128 + qtr * 32 < N) {
+        uint32_t a[32];
+        VALOR_TMEM_LD32(lane_t + TB_DKV + (kt & 1) * 64 + half * 32, a);
+        tmem_wait_ld();
+        if (key < N) {
+          const float mul = half == 0 ? P.scale : 1.0f;
+          bf16* dst = P.dqkv + (size_t)S.qrow[key] * P.lddqkv + (half == 0 ? C : 2 * C) + h * HD;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(a[g * 8 + 0]) * mul, __uint_as_float(a[g * 8 + 1]) * mul);
+            w.y = pack_bf16(__uint_as_float(a[g * 8 + 2]) * mul, __uint_as_float(a[g * 8 + 3]) * mul);
+            w.z = pack_bf16(__uint_as_float(a[g * 8 + 4]) * mul, __uint_as_float(a[g * 8 + 5]) * mul);
+            w.w = pack_bf16(__uint_as_float(a[g * 8 + 6]) * mul, __uint_as_float(a[g * 8 + 7]) * mul);
+            *(uint4*)(dst + g * 8) = w;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    // ---------------- merge the private gradient slices of this k-tile into the CTA table
+    if (want_dtab) {
+      named_bar(5, 256);
+      // slice of warp w: slot byte offsets [lo(w), lo(w) + gt_bytes); lo depends on the warp's key half only
+      int lo[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int kf = kt * 128 + c * 64;
+        lo[c] = kf < N ? 4 * P.maxcode - (int)S.kcode[min(kf + 63, N - 1)] : (1 << 30);
+      }
+      const uint32_t gp = s_u32(S.gpriv);
+      for (int sb = 4 * et; sb < 4 * P.n_used; sb += 4 * 256) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const int off = sb - lo[w >> 2];
+          if (off >= 0 && off < P.gt_bytes) {
+            const uint32_t a = gp + (uint32_t)(w * P.gt_bytes + off);
+            acc += ldv_f32(a);
+            stv_f32(a, 0.f);
+          }
+        }
+        S.ctab[sb >> 2] += acc;
+      }
+      named_bar(5, 256);
+    }
+  }
+  // ---------------- dQ: every k-tile has been accumulated
+  bar_wait(&bars[B_QFULL], 0);
+  tc_fence_after();
+  for (int qt = 0; qt < P.nqt; ++qt) {
+    const int q = qt * 128 + rloc;
+    if (qt * 128 + qtr * 32 < N) {
+      uint32_t a[16];
+      VALOR_TMEM_LD16(lane_t + TB_DQ + qt * 32 + half * 16, a);
+      tmem_wait_ld();
+      if (q < N) {
+        bf16* dst = P.dqkv + (size_t)S.qrow[q] * P.lddqkv + h * HD + half * 16;
+        uint4 w0, w1;
+        w0.x = pack_bf16(__uint_as_float(a[0]) * P.scale, __uint_as_float(a[1]) * P.scale);
+        w0.y = pack_bf16(__uint_as_float(a[2]) * P.scale, __uint_as_float(a[3]) * P.scale);
+        w0.z = pack_bf16(__uint_as_float(a[4]) * P.scale, __uint_as_float(a[5]) * P.scale);
+        w0.w = pack_bf16(__uint_as_float(a[6]) * P.scale, __uint_as_float(a[7]) * P.scale);
+        w1.x = pack_bf16(__uint_as_float(a[8]) * P.scale, __uint_as_float(a[9]) * P.scale);
+        w1.y = pack_bf16(__uint_as_float(a[10]) * P.scale, __uint_as_float(a[11]) * P.scale);
+        w1.z = pack_bf16(__uint_as_float(a[12]) * P.scale, __uint_as_float(a[13]) * P.scale);
+        w1.w = pack_bf16(__uint_as_float(a[14]) * P.scale, __uint_as_float(a[15]) * P.scale);
+        *(uint4*)dst = w0;
+        *(uint4*)(dst + 8) = w1;
+      }
+    }
+  }
+  tc_fence_before();
+  if (want_dtab) {
+    const int r0 = P.center - P.maxcode;
+    for (int r = et; r < P.n_used; r += 256) {
+      const float v = S.ctab[r];
+      if (v != 0.f) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(384, 1)
+window_bwd_sm100_kernel(BwdParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const BwdSmem S = bwd_carve(smem_raw, P);
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = P.heads * HD, col0 = h * HD;
+  const int N = P.win.N;
+  uint64_t* bars = S.bars;
+  if (threadIdx.x == 0) {
+    bar_init(&bars[B_SFULL], 1); bar_init(&bars[B_SFULL + 1], 1);
+    bar_init(&bars[B_SFREE], 4); bar_init(&bars[B_SFREE + 1], 4);
+    bar_init(&bars[B_PDFULL], 8); bar_init(&bars[B_PDFREE], 1);
+    bar_init(&bars[B_KVFULL], 1); bar_init(&bars[B_KVFULL + 1], 1);
+    bar_init(&bars[B_KVLOAD], 64); bar_init(&bars[B_QFULL], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(S.tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  const bool masked = build_tables(P.win, P.maxcode, P.center, P.n_used, p, h, S.qrow, S.qcode, S.kcode, S.qreg, S.tab2, 512);
+  if (P.dtable != nullptr) {
+    float* z = S.ctab;
+    const int nz = (int)(((size_t)P.n_used * 4 + 15) / 16 * 4) + 8 * P.gt_bytes / 4;   // CTA table + private slices (contiguous)
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0.f;
+  }
+  __syncthreads();
+  gather_rows(S.Qs, P.qkv, P.ld, col0, S.qrow, P.nqt * 128);
+  gather_rows(S.dOs, P.dO, P.ldo, col0, S.qrow, P.nqt * 128);
+  gather_rows(S.Ks, P.qkv + C, P.ld, col0, S.qrow, 128);
+  gather_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.qrow, 128);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) S.ld2[2 * i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] * kLog2e : INFINITY;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // -delta_i = -(dO_i . O_i): dO from the staged tile, O rows straight from global memory; four lanes per row
+  for (int c = threadIdx.x; c < 512 * 4; c += blockDim.x) {
+    const int r = c >> 2, ch = c & 3;
+    const int gr = S.qrow[r];
+    float d = 0.f;
+    if (gr >= 0) {
+      const uint4 o4 = *(const uint4*)(P.O + (size_t)gr * P.ldo + col0 + ch * 8);
+      const uint4 a = *(const uint4*)(S.dOs + tile64(r, ch));
+      const __nv_bfloat162* pa = (const __nv_bfloat162*)&a;
+      const __nv_bfloat162* po = (const __nv_bfloat162*)&o4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = __bfloat1622float2(pa[j]), fo = __bfloat1622float2(po[j]);
+        d += fa.x * fo.x + fa.y * fo.y;
+      }
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    if (ch == 0) S.ld2[2 * r + 1] = -d;
+  }
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *S.tmem_slot;
+  const int nb = P.nkt * P.nqt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t Qs = s_u32(S.Qs), dOs = s_u32(S.dOs), Ks = s_u32(S.Ks), Vs = s_u32(S.Vs), Pb = s_u32(S.Pb), dSb = s_u32(S.dSb);
+      const uint32_t id_s = make_idesc(64, 0, 0), id_kv = make_idesc(HD, 1, 1), id_q = make_idesc(HD, 0, 1);
+      auto issue_s = [&](int b) {
+        const int qt = b % P.nqt;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (b > 0) { bar_wait(&bars[B_SFREE + hf], (b - 1) & 1); tc_fence_after(); }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            tc_mma(tmem + TB_S + hf * 64, smem_desc(Qs + qt * 128 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4),
+                   smem_desc(Ks + hf * 64 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4), id_s, k);
+            tc_mma(tmem + TB_DP + hf * 64, smem_desc(dOs + qt * 128 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4),
+                   smem_desc(Vs + hf * 64 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4), id_s, k);
+          }
+          tc_commit(&bars[B_SFULL + hf]);
+        }
+      };
+      issue_s(0);
+      for (int b = 0; b < nb; ++b) {
+        const int kt = b / P.nqt, qt = b % P.nqt;
+        const bool more = b + 1 < nb;
+        const bool same_tile = more && (b + 1) / P.nqt == kt;
+        if (same_tile) issue_s(b + 1);
+        bar_wait(&bars[B_PDFULL], b & 1);
+        tc_fence_after();
+        const int kq = (min(128, N - qt * 128) + 15) / 16;       // 16-query k-steps that hold real rows
+        const int kk = (min(128, N - kt * 128) + 15) / 16;       // 16-key k-steps that hold real keys
+        const uint32_t tkv = tmem + TB_DKV + (kt & 1) * 64;
+        for (int ks = 0; ks < kq; ++ks) {
+          const uint64_t bq = smem_desc(Qs + (qt * 128 + ks * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4);
+          const uint64_t bo = smem_desc(dOs + (qt * 128 + ks * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4);
+          const uint32_t acc = (qt | ks) ? 1u : 0u;
+          tc_mma(tkv, smem_desc(dSb + ks * 2048, 16384, 1024, 2), bq, id_kv, acc);        // dK += dS^T . Q
+          tc_mma(tkv + 32, smem_desc(Pb + ks * 2048, 16384, 1024, 2), bo, id_kv, acc);    // dV += P^T . dO
+        }
+        for (int ks = 0; ks < kk; ++ks)                                                   // dQ += dS . K
+          tc_mma(tmem + TB_DQ + qt * 32, smem_desc(dSb + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024, 2),
+                 smem_desc(Ks + ks * 16 * ROWB, VALOR_SW64_MN_LBO, 512, 4), id_q, (kt | ks) ? 1u : 0u);
+        tc_commit(&bars[B_PDFREE]);
+        if (qt == P.nqt - 1) tc_commit(&bars[B_KVFULL + (kt & 1)]);
+        if (more && !same_tile) {
+          bar_wait(&bars[B_KVLOAD], kt & 1);      // next K / V tile has landed
+          tc_fence_after();
+          issue_s(b + 1);
+        }
+      }
+      tc_commit(&bars[B_QFULL]);
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== K / V tile loader (64 threads) =====================
+    const int lt = threadIdx.x - 64;
+    for (int kt = 1; kt < P.nkt; ++kt) {
+      bar_wait(&bars[B_KVFULL + ((kt - 1) & 1)], ((kt - 1) >> 1) & 1);   // every MMA that reads the previous tile has retired
+      const uint32_t k0 = s_u32(S.Ks), v0 = s_u32(S.Vs);
+      for (int c = lt; c < 128 * 4; c += 64) {
+        const int r = c >> 2, ch = c & 3;
+        const int gr = S.qrow[kt * 128 + r];
+        const bf16* src = P.qkv + (size_t)(gr < 0 ? 0 : gr) * P.ld + col0 + ch * 8;
+        cp_async16(k0 + tile64(r, ch), src + C, gr < 0 ? 0 : 16);
+        cp_async16(v0 + tile64(r, ch), src + 2 * C, gr < 0 ? 0 : 16);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      proxy_fence();
+      bar_arrive(&bars[B_KVLOAD]);
+    }
+  } else if (warp >= 4) {
+    if (masked) bwd_element_warps<true>(P, S, h, tmem);
+    else bwd_element_warps<false>(P, S, h, tmem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static void sm100_geometry(const WindowIndex& ix, int& nqt, int& NPK, int& np, int& maxcode, int& center, int& n_used) {
+  nqt = (ix.N + 127) / 128;
+  NPK = (ix.N + 15) / 16 * 16;
+  np = (NPK + 63) / 64;
+  const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
+  center = (ix.WD - 1) * cH + (ix.WH - 1) * cW + (ix.WW - 1);
+  maxcode = (ix.wd - 1) * cH + (ix.wh - 1) * cW + (ix.ww - 1);
+  n_used = 2 * maxcode + 1;
+}
+
+bool window_sm100_fwd_eligible(const WindowIndex& ix, int hd) {
+  if (hd != HD || ix.N > 448 || ix.N < 1 || ix.wh * ix.ww > 256) return false;   // S needs N <= 448 tensor-memory columns
+  int nqt, NPK, np, maxcode, center, n_used;
+  sm100_geometry(ix, nqt, NPK, np, maxcode, center, n_used);
+  return fwd_smem_bytes(nqt, NPK, np, n_used) <= 227 * 1024;
+}
+
+int window_sm100_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
+                     int H, int hd, float scale, cudaStream_t st) {
+  VALOR_REQUIRE(window_sm100_fwd_eligible(ix, hd), "window_sm100_fwd: geometry not eligible");
+  FwdParams P = {};
+  sm100_geometry(ix, P.nqt, P.NPK, P.np, P.maxcode, P.center, P.n_used);
+  P.win = ix; P.heads = H;
+  P.qkv = (const bf16*)qkv; P.ld = ld; P.O = (bf16*)O; P.ldo = ldo; P.lse = lse; P.scale2 = scale * kLog2e;
+  const size_t smem = fwd_smem_bytes(P.nqt, P.NPK, P.np, P.n_used);
+  static size_t attr = 0;
+  if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  window_fwd_sm100_kernel<<<dim3(Pn, H), 384, smem, st>>>(P);
+  return check_launch("window_fwd_sm100_kernel");
+}
+
+// bytes of one element warp's private gradient slice: 4 * (maxcode + widest code span of an aligned 64-token range + 1)
+static int bwd_gt_bytes(const WindowIndex& ix, int maxcode) {
+  const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
+  auto code = [&](int i) { return (i / (ix.wh * ix.ww)) * cH + ((i / ix.ww) % ix.wh) * cW + i % ix.ww; };
+  int span = 0;
+  for (int f = 0; f < ix.N; f += 64) span = std::max(span, code(std::min(f + 63, ix.N - 1)) - code(f));
+  return (4 * (maxcode + span + 1) + 15) / 16 * 16;
+}
+
+bool window_sm100_bwd_eligible(const WindowIndex& ix, int hd, bool want_dtab) {
+  if (hd != HD || ix.N > 512 || ix.N < 1 || ix.wh * ix.ww > 256) return false;
+  int nqt, NPK, np, maxcode, center, n_used;
+  sm100_geometry(ix, nqt, NPK, np, maxcode, center, n_used);
+  return bwd_smem_bytes(nqt, n_used, bwd_gt_bytes(ix, maxcode), want_dtab) <= 227 * 1024;
+}
+
+int window_sm100_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
+                     const float* lse, void* dqkv, long long lddqkv, float* dtable, int Pn, int H, int hd, float scale,
+                     cudaStream_t st) {
+  VALOR_REQUIRE(window_sm100_bwd_eligible(ix, hd, dtable != nullptr), "window_sm100_bwd: geometry not eligible");
+  BwdParams P = {};
+  int NPK, np;
+  sm100_geometry(ix, P.nqt, NPK, np, P.maxcode, P.center, P.n_used);
+  P.nkt = P.nqt;
+  P.win = ix; P.heads = H;
+  P.qkv = (const bf16*)qkv; P.ld = ld; P.O = (const bf16*)O; P.dO = (const bf16*)dO; P.ldo = ldo; P.lse = lse;
+  P.dqkv = (bf16*)dqkv; P.lddqkv = lddqkv; P.dtable = dtable; P.scale = scale; P.scale2 = scale * kLog2e;
+  P.gt_bytes = bwd_gt_bytes(ix, P.maxcode);
+  const size_t smem = bwd_smem_bytes(P.nqt, P.n_used, P.gt_bytes, dtable != nullptr);
+  static size_t attr = 0;
+  if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  window_bwd_sm100_kernel<<<dim3(Pn, H), 384, smem, st>>>(P);
+  return check_launch("window_bwd_sm100_kernel");
+}
+
+}  // namespace valor

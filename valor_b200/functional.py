@@ -378,17 +378,48 @@ class L2NormFn(Function):
         return K.l2norm_bwd(dy, x, nrm)
 
 
+class CastFn(Function):
+    """dtype change between the fp32 contrastive head and the low-precision GEMM operands"""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        if x.dtype == dtype:
+            return x.view_as(x)
+        y = torch.empty(x.shape, device=x.device, dtype=dtype)
+        K.cast2d(x.contiguous(), y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy.dtype == ctx.src:
+            return dy, None
+        dx = torch.empty(dy.shape, device=dy.device, dtype=ctx.src)
+        K.cast2d(dy.contiguous(), dx)
+        return dx, None
+
+
 class FineSimFn(Function):
     """compute_fine_matrix for the three modality groups at once (pretrain.py:178-211,302-345).
+    split_operands: features are fp32 and the similarity GEMM runs on the bf16 tensor cores through the two-term
+    expansion of both operands (valor_split_bf16x3), i.e. with fp32-grade dot products.
     feat_t [Na*T, D], feat_va [Nb*Vt, D] (per sample: video slots then audio slots),
     w_t [Na,T], w_v [Nb,nV], w_a [Nb,nA] raw fine weights (fp32), maskA [Na,T] uint8.
     Returns scores [G, Na, Nb] for groups tva / tv / ta (those requested)."""
 
     @staticmethod
-    def forward(ctx, feat_t, feat_va, w_t, w_v, w_a, maskA, dims, groups):
+    def forward(ctx, feat_t, feat_va, w_t, w_v, w_a, maskA, dims, groups, split_operands=False):
         Na, Nb, T, nV, nA = dims
         Vt = nV + nA
-        L = K.gemm(feat_t.contiguous(), feat_va.contiguous(), out_dtype=torch.float32)  # [Na*T, Nb*Vt]
+        ctx_lp = None
+        if split_operands:
+            # perf mode: fp32 features, bf16 tensor cores: two-term expansion of both operands, ONE GEMM over K = 3D
+            ta, vb = K.split_bf16x3(feat_t.contiguous(), 0), K.split_bf16x3(feat_va.contiguous(), 1)
+            L = K.gemm(ta, vb, out_dtype=torch.float32)                                # [Na*T, Nb*Vt]
+            ctx_lp = (ta, vb)
+        else:
+            L = K.gemm(feat_t.contiguous(), feat_va.contiguous(), out_dtype=torch.float32)
+        ctx.lp = ctx_lp
         wsA = K.masked_softmax_fwd(w_t, maskA)
         scores, saved = [], []
         for g in groups:
@@ -425,6 +456,14 @@ class FineSimFn(Function):
             else:
                 dw_a += dwB
         dw_t = K.masked_softmax_bwd(wsA, dwsA)
+        if ctx.lp is not None:      # gradients through the leading (hi) terms of the expansions, fp32 out
+            ta, vb = ctx.lp
+            D = feat_t.shape[1]
+            dLl = torch.empty(dL.shape, device=dL.device, dtype=ta.dtype)
+            K.cast2d(dL, dLl)
+            dft = K.gemm(dLl, vb[:, :D], b_kmajor=False, out_dtype=torch.float32)
+            dfva = K.gemm(dLl, ta[:, :D], a_kmajor=False, b_kmajor=False, out_dtype=torch.float32)
+            return dft, dfva, dw_t, dw_v, dw_a, None, None, None, None
         if feat_t.dtype != torch.float32:
             dLl = torch.empty(dL.shape, device=dL.device, dtype=feat_t.dtype)
             K.cast2d(dL, dLl)
@@ -432,7 +471,7 @@ class FineSimFn(Function):
             dLl = dL
         dft = K.gemm(dLl, feat_va, b_kmajor=False)
         dfva = K.gemm(dLl, feat_t, a_kmajor=False, b_kmajor=False)
-        return dft, dfva, dw_t, dw_v, dw_a, None, None, None
+        return dft, dfva, dw_t, dw_v, dw_a, None, None, None, None
 
 
 class ContrastiveFn(Function):

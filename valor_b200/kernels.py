@@ -11,7 +11,7 @@ from . import _lib
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3
-BACKEND_AUTO, BACKEND_TENSOR, BACKEND_SIMT = 0, 1, 2
+BACKEND_AUTO, BACKEND_TENSOR, BACKEND_SIMT, BACKEND_MMA_SYNC = 0, 1, 2, 3
 
 launch_count = 0  # kernels-launched-through-the-ABI counter (bench.py's gpu_launches)
 
@@ -285,6 +285,15 @@ def cast_flat(src, dst):
     n = src.numel()
     assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous()
     _call("valor_cast2d", DT(src), DT(dst), P(src), n, P(dst), n, 1, n, ST())
+
+
+def split_bf16x3(x, side):
+    """x [R,C] fp32 -> [R,3C] bf16 two-term expansion ([hi|hi|lo] for side 0, [hi|lo|hi] for side 1)."""
+    R, C = x.shape
+    assert x.dtype == torch.float32
+    out = torch.empty(R, 3 * C, device=x.device, dtype=torch.bfloat16)
+    _call("valor_split_bf16x3", P(x), _ld(x), P(out), R, C, side, ST())
+    return out
 
 
 def act_bwd(dy, h, act):

@@ -89,7 +89,7 @@ class VALOR(VALORModel):
 
     def _fine_weight(self, feat, name):
         seq = getattr(self, f"{name}_fine_weight")
-        h = Fn.linear(feat, lin_of(seq[0].weight, seq[0].bias), act=K.ACT_RELU)
+        h = Fn.linear(Fn.CastFn.apply(feat, self.compute_dtype), lin_of(seq[0].weight, seq[0].bias), act=K.ACT_RELU)
         return Fn.linear(h, lin_of(seq[2].weight, seq[2].bias), out_dtype=torch.float32)  # [rows, 1] fp32
 
     def forward_pt(self, batch, task, compute_loss=True):
@@ -115,7 +115,11 @@ class VALOR(VALORModel):
 
         if contra_task:
             txt_output = self.forward_txt_encoder(txt_tokens)                                   # [B,T,768]
-            feat_t = Fn.L2NormFn.apply(Fn.linear(txt_output.reshape(B * T, -1), lin_of(self.contra_head_t.linear.weight)))
+            # the contrastive head runs in fp32 from the projection on (features, L2 normalisation, all-gather, fine
+            # similarity): the loss divides similarities by temp = 0.07, so bf16-rounded unit features alone would cost
+            # ~2e-3 of the loss; the GEMMs still run on the bf16 tensor cores (split operands, FineSimFn)
+            f32 = torch.float32
+            feat_t = Fn.L2NormFn.apply(Fn.linear(txt_output.reshape(B * T, -1), lin_of(self.contra_head_t.linear.weight), out_dtype=f32))
             feat_t = ddp_allgather_with_grads.apply(feat_t.view(B, T, -1))
             tokens_g = ddp_allgather(txt_tokens)
             Na = feat_t.shape[0]
@@ -124,12 +128,12 @@ class VALOR(VALORModel):
             if "v" in "".join(contra_task):
                 _, nV, X, C = video_output.shape
                 pooled = Fn.MeanPoolFn.apply(video_output.reshape(-1, C), B * nV, X)        # modeling.py:389
-                feat_v = Fn.L2NormFn.apply(Fn.linear(pooled, lin_of(self.contra_head_v.linear.weight)))
+                feat_v = Fn.L2NormFn.apply(Fn.linear(pooled, lin_of(self.contra_head_v.linear.weight), out_dtype=f32))
                 feat_v = ddp_allgather_with_grads.apply(feat_v.view(B, nV, -1))
             if "a" in "".join(contra_task):
                 _, nA, X, C = audio_output.shape
                 cls = Fn.SelectFirstFn.apply(audio_output.reshape(-1, C), B * nA, X)        # modeling.py:399
-                feat_a = Fn.L2NormFn.apply(Fn.linear(cls, lin_of(self.contra_head_a.linear.weight)))
+                feat_a = Fn.L2NormFn.apply(Fn.linear(cls, lin_of(self.contra_head_a.linear.weight), out_dtype=f32))
                 feat_a = ddp_allgather_with_grads.apply(feat_a.view(B, nA, -1))
             D = feat_t.shape[-1]
             w_t = self._fine_weight(feat_t.reshape(Na * T, D), "text").view(Na, T)
@@ -143,7 +147,7 @@ class VALOR(VALORModel):
             maskA = (tokens_g != 0).to(torch.uint8).contiguous()                               # pretrain.py:304
             groups = [g for g in ("tva", "tv", "ta") if g in contra_task]                      # order of pretrain.py:397
             scores = Fn.FineSimFn.apply(feat_t.reshape(Na * T, D), feat_va.reshape(-1, D), w_t, w_v, w_a, maskA,
-                                        (Na, Na, T, nV, nA), groups)
+                                        (Na, Na, T, nV, nA), groups, dt != torch.float32)
             lo = [Fn.ContrastiveFn.apply(scores[i], self.contra_temp) for i in range(len(groups))]
             loss_dict["contra_loss"] = (sum(lo) / len(lo) * self.contra_loss_ratio).reshape(())
 
