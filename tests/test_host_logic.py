@@ -136,3 +136,21 @@ def test_forward_backward_matches_reference_golden(cpu_kernels, name):
             continue
         assert abs(g.norm().item() - ref["norm"]) <= 1e-3 * ref["norm"] + 1e-9, (k, g.norm().item(), ref["norm"])
         torch.testing.assert_close(g.flatten()[:6], torch.tensor(ref["head"]), rtol=5e-3, atol=1e-6)
+
+
+def test_evaluation_dict_matches_reference_logits(cpu_kernels):
+    """compute_loss=False (pretrain.py:402-406,446,463,480,485): features, tokens, per-pass masked-token scores, labels"""
+    golden = json.load(open(os.path.join(HERE, "golden", "golden_tiny.json")))
+    model, batch = build(golden["config"])
+    with torch.no_grad():
+        ev = model(batch, golden["config"]["task"], compute_loss=False)
+    cfg = golden["config"]
+    assert ev["feat_t"].shape == (cfg["B"], cfg["T"], 512) and ev["feat_v"].shape == (cfg["B"], cfg["F"], 512)
+    assert ev["feat_a"].shape == (cfg["B"], cfg["A"], 512) and torch.equal(ev["txt_tokens"], batch["txt_tokens"]["bert_tokens"])
+    torch.testing.assert_close(ev["feat_t"].norm(dim=-1), torch.ones(cfg["B"], cfg["T"]), rtol=1e-5, atol=1e-5)
+    for nm, ref in golden["logits"].items():
+        sc = ev[f"caption_scores_{nm}"].float()
+        assert sc.shape[0] == ref["n_rows"]
+        rows = len(ref["lse"])
+        torch.testing.assert_close(sc[:rows, :8], torch.tensor(ref["head"]), rtol=3e-4, atol=3e-4)
+    assert (ev["txt_labels_caption"] != -1).sum().item() == golden["logits"]["tva"]["n_rows"]

@@ -93,12 +93,16 @@ class VALOR(VALORModel):
         return Fn.linear(h, lin_of(seq[2].weight, seq[2].bias), out_dtype=torch.float32)  # [rows, 1] fp32
 
     def forward_pt(self, batch, task, compute_loss=True):
-        """pretrain.py:214-541 for compute_loss=True."""
-        assert compute_loss, "evaluation dict path is not part of the training hot path"
+        """pretrain.py:214-541.  compute_loss=True -> {'contra_loss','caption_loss'}; compute_loss=False -> the
+        reference's evaluation dict (:402-406,:446,:480,:541): L2-normalised contrastive features (local rows, no
+        all-gather), the contrastive tokens, per-pass masked-token caption scores and the caption labels."""
         contra_task, caption_task = [], []
         for t in task.split("_"):
             if "mlm" in t:
-                raise NotImplementedError("the shipped pretraining task string has no mlm objective")
+                # pretrain.py:487-519 drives the mlm objective through task prompts built by the BERT tokenizer
+                # (modeling.py:355-369) regardless of use_task_prompt; tokenizers and the prompt path are outside the
+                # scope table (SURVEY.md §2), and the shipped pretraining task string has no mlm objective
+                raise NotImplementedError("the mlm objective needs the tokenizer-built task prompts (out of scope)")
             elif "caption" in t:
                 caption_task = t.split("%")[1:]
             elif "contra" in t:
@@ -120,8 +124,10 @@ class VALOR(VALORModel):
             # ~2e-3 of the loss; the GEMMs still run on the bf16 tensor cores (split operands, FineSimFn)
             f32 = torch.float32
             feat_t = Fn.L2NormFn.apply(Fn.linear(txt_output.reshape(B * T, -1), lin_of(self.contra_head_t.linear.weight), out_dtype=f32))
-            feat_t = ddp_allgather_with_grads.apply(feat_t.view(B, T, -1))
-            tokens_g = ddp_allgather(txt_tokens)
+            feat_t = feat_t.view(B, T, -1)
+            if compute_loss:
+                feat_t = ddp_allgather_with_grads.apply(feat_t)
+            tokens_g = ddp_allgather(txt_tokens) if compute_loss else txt_tokens
             Na = feat_t.shape[0]
             nV = nA = 0
             feat_v = feat_a = None
@@ -129,27 +135,34 @@ class VALOR(VALORModel):
                 _, nV, X, C = video_output.shape
                 pooled = Fn.MeanPoolFn.apply(video_output.reshape(-1, C), B * nV, X)        # modeling.py:389
                 feat_v = Fn.L2NormFn.apply(Fn.linear(pooled, lin_of(self.contra_head_v.linear.weight), out_dtype=f32))
-                feat_v = ddp_allgather_with_grads.apply(feat_v.view(B, nV, -1))
+                feat_v = feat_v.view(B, nV, -1)
+                if compute_loss:
+                    feat_v = ddp_allgather_with_grads.apply(feat_v)
             if "a" in "".join(contra_task):
                 _, nA, X, C = audio_output.shape
                 cls = Fn.SelectFirstFn.apply(audio_output.reshape(-1, C), B * nA, X)        # modeling.py:399
                 feat_a = Fn.L2NormFn.apply(Fn.linear(cls, lin_of(self.contra_head_a.linear.weight), out_dtype=f32))
-                feat_a = ddp_allgather_with_grads.apply(feat_a.view(B, nA, -1))
-            D = feat_t.shape[-1]
-            w_t = self._fine_weight(feat_t.reshape(Na * T, D), "text").view(Na, T)
-            dev = feat_t.device
-            w_v = self._fine_weight(feat_v.reshape(Na * nV, D), "video").view(Na, nV) if feat_v is not None else \
-                torch.zeros(Na, 0, device=dev)
-            w_a = self._fine_weight(feat_a.reshape(Na * nA, D), "audio").view(Na, nA) if feat_a is not None else \
-                torch.zeros(Na, 0, device=dev)
-            parts = [f for f in (feat_v, feat_a) if f is not None]
-            feat_va = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]                  # pretrain.py:324
-            maskA = (tokens_g != 0).to(torch.uint8).contiguous()                               # pretrain.py:304
-            groups = [g for g in ("tva", "tv", "ta") if g in contra_task]                      # order of pretrain.py:397
-            scores = Fn.FineSimFn.apply(feat_t.reshape(Na * T, D), feat_va.reshape(-1, D), w_t, w_v, w_a, maskA,
-                                        (Na, Na, T, nV, nA), groups, dt != torch.float32)
-            lo = [Fn.ContrastiveFn.apply(scores[i], self.contra_temp) for i in range(len(groups))]
-            loss_dict["contra_loss"] = (sum(lo) / len(lo) * self.contra_loss_ratio).reshape(())
+                feat_a = feat_a.view(B, nA, -1)
+                if compute_loss:
+                    feat_a = ddp_allgather_with_grads.apply(feat_a)
+            if not compute_loss:
+                loss_dict.update(feat_t=feat_t, feat_v=feat_v, feat_a=feat_a, txt_tokens=tokens_g)      # pretrain.py:402-406
+            else:
+                D = feat_t.shape[-1]
+                w_t = self._fine_weight(feat_t.reshape(Na * T, D), "text").view(Na, T)
+                dev = feat_t.device
+                w_v = self._fine_weight(feat_v.reshape(Na * nV, D), "video").view(Na, nV) if feat_v is not None else \
+                    torch.zeros(Na, 0, device=dev)
+                w_a = self._fine_weight(feat_a.reshape(Na * nA, D), "audio").view(Na, nA) if feat_a is not None else \
+                    torch.zeros(Na, 0, device=dev)
+                parts = [f for f in (feat_v, feat_a) if f is not None]
+                feat_va = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]                  # pretrain.py:324
+                maskA = (tokens_g != 0).to(torch.uint8).contiguous()                               # pretrain.py:304
+                groups = [g for g in ("tva", "tv", "ta") if g in contra_task]                      # order of pretrain.py:397
+                scores = Fn.FineSimFn.apply(feat_t.reshape(Na * T, D), feat_va.reshape(-1, D), w_t, w_v, w_a, maskA,
+                                            (Na, Na, T, nV, nA), groups, dt != torch.float32)
+                lo = [Fn.ContrastiveFn.apply(scores[i], self.contra_temp) for i in range(len(groups))]
+                loss_dict["contra_loss"] = (sum(lo) / len(lo) * self.contra_loss_ratio).reshape(())
 
         if caption_task:
             media, Sv, Sa = self.media_tokens(video_output, audio_output)                       # modeling.py:485-502
@@ -170,5 +183,12 @@ class VALOR(VALORModel):
             labels = txt_labels.repeat_interleave(npass, 0).reshape(-1)
             if getattr(self, "debug_capture", None) is not None:   # parity tests: the masked-token logits
                 self.debug_capture.update(logits=logits.detach().clone(), labels=labels, npass=npass, names=names)
-            loss_dict["caption_loss"] = Fn.XentFn.apply(logits, labels).reshape(())
+            if compute_loss:
+                loss_dict["caption_loss"] = Fn.XentFn.apply(logits, labels).reshape(())
+            else:   # pretrain.py:446,463,480,485: scores of the masked positions, per pass, plus the labels
+                lg = logits.view(B, npass, T, -1)
+                sel = txt_labels != -1
+                for i, n in enumerate(names):
+                    loss_dict[f"caption_scores_{n}"] = lg[:, i][sel]
+                loss_dict["txt_labels_caption"] = txt_labels
         return loss_dict
