@@ -77,6 +77,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-the-same-GPU competitor leg")
     ap.add_argument("--cpu-trial", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--no-dropout", action="store_true",
+                    help="parity mode: Dropout / DropPath disabled (default: the reference's training regularisation is ON)")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -351,6 +353,8 @@ def main():
                         num_train_steps=1000)
     model = VALOR.from_pretrained(opts, synth.make_state_dict(geom, seed=0))
     store = model.attach(dtype=torch.bfloat16, device=dev)
+    stochastic = not args.no_dropout
+    model.set_stochastic(stochastic, seed=1234 + rank)
     host = synth.make_batch(B, F, A, T, geom, seed=123 + rank)
     tokens_h = host["txt_tokens"]["bert_tokens"]
     mask_h = synth.token_masker(tokens_h, 0.6, seed=1234 + rank)   # host-side draw (TokenMasker is host code)
@@ -471,6 +475,8 @@ def main():
                 gstep[0] += 1
                 store.set_hyper(get_lr_sched(gstep[0], opts), base_lr=opts.learning_rate, betas=tuple(opts.betas),
                                 weight_decay=opts.weight_decay)
+                if model.rng.active:
+                    model.rng.advance()          # 16-byte H2D: the replay draws fresh Dropout / DropPath masks
                 graph.replay()
                 return static_losses
             log(f"CUDA graph captured: {graph_launches} ABI launches per step")
@@ -544,6 +550,34 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     log(f"e2e: {ms_e2e:.2f} ms/step")
 
+    parity_mode = None
+    if stochastic and graph is not None:
+        try:   # the same step with Dropout / DropPath disabled (the configuration the parity tests pin), for reference
+            model.set_stochastic(False)
+            g2 = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body(resident)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g2):
+                body(resident)
+
+            def parity_step():
+                gstep[0] += 1
+                store.set_hyper(get_lr_sched(gstep[0], opts), base_lr=opts.learning_rate, betas=tuple(opts.betas),
+                                weight_decay=opts.weight_decay)
+                g2.replay()
+            for _ in range(3):
+                parity_step()
+            ms_p, _ = timed(parity_step, args.steps)
+            parity_mode = {"ms_per_step": ms_p, "value": world * B / (ms_p * 1e-3), "unit": "samples/s",
+                           "note": "Dropout / DropPath off (the configuration of the parity tests)"}
+            del g2
+            model.set_stochastic(True)
+        except Exception as ex:  # pragma: no cover
+            log(f"parity-mode timing failed: {type(ex).__name__}: {ex}")
     value = world * B / (ms_step * 1e-3)
     e2e_val = world * B / (ms_e2e * 1e-3)
     line = {"metric": "pretrain samples/sec (video+audio+text)", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -551,7 +585,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"VALOR-base (VideoSwin-B + AST + BERT-base fusion) pretrain step, per-GPU batch {B}, "
                                    f"{F} frames 224^2, {A} audio clips, {T} tokens (BASELINE configs[1])",
-                       "task": TASK, "global_batch": world * B, "parallelism": f"dp{world}", "dropout": "off (parity mode)",
+                       "task": TASK, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "dropout": ("on: hidden Dropout 0.1 (BERT, AST) + DropPath 0->0.2 (VideoSwin), masks regenerated in "
+                                   "the backward; attention-probability dropout not applied") if stochastic else
+                                  "off (parity mode)",
                        "l2": "inputs larger than L2 (154 MB pixels/step), weights+activations >> 126 MB",
                        "geom": args.geom},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
@@ -559,6 +596,8 @@ def main():
                     "pipeline": "H2D of step i+1 on a copy stream during step i (PrefetchLoader semantics), losses read back every step"},
             "gpu_launches": launches, "cuda_graph": graph is not None, "clocks": clocks, "losses": loss_vals,
             "step_mfu": FLOPS_PER_SAMPLE * B / (ms_step * 1e-3) / (peak_tf * 1e12) if args.geom == "base" else None}
+    if parity_mode:
+        line["parity_mode"] = parity_mode
     if roof:
         roof["gemm_share_of_step"] = roof["gemm_ms_per_step"] / ms_step
         line["roofline"] = roof

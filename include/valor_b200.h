@@ -151,6 +151,19 @@ int valor_cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, v
  * [hi|lo|hi] (side 1), so one tcgen05 GEMM over K = 3C gives fp32-grade dot products of the L2-normalised contrastive
  * features: torch.einsum('atd,bvd->abtv') of compute_fine_matrix_slice (pretrain.py:200) in the reference's fp32 */
 int valor_split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, void* stream);
+/* ---- training-mode regularisation ---------------------------------------------------------------------------------
+ * nn.Dropout(p) of BERT / AST hidden states (bert.py:217,353,367,418; transformer.py:78,83; modeling.py:761) fused with the
+ * residual add that follows it:  out = residual + x * keep / (1-p)  (residual NULL: plain dropout; the backward of the
+ * dropped branch is the same call on dy with residual NULL).  The keep mask is regenerated from Philox4x32-10 keyed by
+ * rng_state = {seed, step offset} (int64[2] in DEVICE memory, rewritten by the host once per step so captured graphs see new
+ * masks), the call-site id `site` and the element index r*C + c: nothing is stored between forward and backward. */
+int valor_dropout(int dtype, const void* x, long long ldx, const void* residual, long long ldr, void* out, long long ldo, long long R,
+                  int C, float p, const long long* rng_state, long long site, void* stream);
+/* DropPath (videoswin.py:40-55): scale[b] = floor(1-p + u_b) / (1-p), one uniform per sample */
+int valor_droppath_scale(float* scale, int B, float p, const long long* rng_state, long long site, void* stream);
+/* out[r,:] = residual[r,:] + x[r,:] * scale[r / rows_per_group]   (videoswin.py:238,243; residual NULL in the backward) */
+int valor_row_scale(int dtype, const void* x, long long ldx, const float* scale, long long rows_per_group, const void* residual,
+                    long long ldr, void* out, long long ldo, long long R, int C, void* stream);
 /* dh = dy * act'(h): gradient through GELU / QuickGELU / ReLU where it cannot ride a GEMM epilogue */
 int valor_act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, void* stream);
 int valor_strided_rows(int dtype, const void* src, long long sld, void* dst, long long dld, long long R, int C, int accumulate, void* stream);

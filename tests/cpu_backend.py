@@ -306,6 +306,34 @@ def colsum(dy, db):
     db += dy.float().sum(0)
 
 
+def _keep_mask(shape, p, rng_state, site):
+    g = torch.Generator().manual_seed(int(rng_state[0]) * 1000003 + int(rng_state[1]) * 7919 + int(site))
+    return (torch.rand(shape, generator=g) >= p).float()
+
+
+def dropout(x, residual, p, rng_state, site, out=None):
+    y = x.float() * _keep_mask(x.shape, p, rng_state, site) / (1.0 - p)
+    if residual is not None:
+        y = y + residual.float()
+    y = y.to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def droppath_scale(B, p, rng_state, site):
+    g = torch.Generator().manual_seed(int(rng_state[0]) * 1000003 + int(rng_state[1]) * 7919 + int(site))
+    return torch.floor(1.0 - p + torch.rand(B, generator=g)) / (1.0 - p)
+
+
+def row_scale(x, scale, rows_per_group, residual=None):
+    y = x.float() * scale.repeat_interleave(rows_per_group)[:, None]
+    if residual is not None:
+        y = y + residual.float()
+    return y.to(x.dtype)
+
+
 def split_bf16x3(x, side):
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16)

@@ -109,7 +109,8 @@ def run(name, geom, B, F, A, T, task=TASK):
         if kk not in named:  # shared module is registered under its first name
             continue
         g = named[kk].grad
-        out["grads"][k] = None if g is None else {"norm": g.norm().item(), "head": g.flatten()[:6].tolist()}
+        # float64 norms: torch's CPU fp32 reduction loses ~1e-3 on the 23 M-element embedding matrix
+        out["grads"][k] = None if g is None else {"norm": g.double().norm().item(), "head": g.flatten()[:6].tolist()}
     out["unused_params"] = sorted(k for k, p in named.items() if p.grad is None)
     out["n_params"] = sum(p.numel() for p in named.values())
     if name in TRAJECTORY:
@@ -158,7 +159,7 @@ def trajectory(model, batch, n_steps, task=TASK):
     with ref_shim.cuda_identity(), torch.no_grad():
         loss_dict = model(batch, task, compute_loss=True)
     rec["final_losses"] = {k: v.item() for k, v in loss_dict.items()}
-    rec["params"] = {k: {"norm": named[k].detach().norm().item(), "head": named[k].detach().flatten()[:6].tolist()}
+    rec["params"] = {k: {"norm": named[k].detach().double().norm().item(), "head": named[k].detach().flatten()[:6].tolist()}
                      for k in GRAD_KEYS + ["multimodal_encoder.pooler.dense.weight"] if k in named}
     return rec
 

@@ -424,3 +424,43 @@ def test_adamw_against_reference_formula():
     assert abs(norm[0].item() - total.item()) <= 1e-4 * total.item()
     close(pd, pr, torch.float32, "adamw p")
     close(lp, pr, torch.bfloat16, "adamw bf16 copy")
+
+
+# ------------------------------------------------------------------------------------------
+# stochastic regularisation (Dropout / DropPath): counter-based masks regenerated in the backward
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dropout_masks_are_regenerated_and_unbiased(dtype):
+    k = K()
+    R, C, p = 4096, 768, 0.1
+    st = torch.tensor([1234, 1 << 24], dtype=torch.int64, device="cuda")
+    x = torch.ones(R, C, device="cuda", dtype=dtype)
+    res = torch.full((R, C), 2.0, device="cuda", dtype=dtype)
+    y = k.dropout(x, None, p, st, 7)
+    keep = (y != 0).float()
+    assert abs(keep.mean().item() - (1 - p)) < 3e-3                         # 3.1M draws: sigma ~ 1.7e-4
+    vals = y[y != 0].float().unique()
+    assert len(vals) == 1 and abs(vals.item() - 1 / (1 - p)) < 1e-2         # kept entries scaled by 1/(1-p)
+    assert torch.equal(k.dropout(x, None, p, st, 7), y)                     # same {state, site} -> same mask (backward)
+    y2 = k.dropout(x, res, p, st, 7)
+    torch.testing.assert_close(y2.float(), y.float() + 2.0, rtol=1e-2, atol=1e-2)
+    assert not torch.equal(k.dropout(x, None, p, st, 8), y)                 # another call site
+    st2 = torch.tensor([1234, 2 << 24], dtype=torch.int64, device="cuda")
+    assert not torch.equal(k.dropout(x, None, p, st2, 7), y)                # another step
+    # rows / columns are not correlated: per-row and per-column keep rates stay near 1-p
+    assert (keep.mean(dim=1) - (1 - p)).abs().max().item() < 0.06 and (keep.mean(dim=0) - (1 - p)).abs().max().item() < 0.03
+
+
+def test_droppath_scale_and_row_scale():
+    k = K()
+    st = torch.tensor([5, 3 << 24], dtype=torch.int64, device="cuda")
+    sc = k.droppath_scale(4096, 0.2, st, 3)
+    assert set(torch.round(sc * 1000).long().unique().tolist()) <= {0, 1250}        # {0, 1/keep_prob}, videoswin.py:45-50
+    assert abs((sc > 0).float().mean().item() - 0.8) < 0.03
+    x = rnd(8 * 49, 128, dtype=torch.bfloat16, seed=1)
+    r = rnd(8 * 49, 128, dtype=torch.bfloat16, seed=2)
+    s8 = torch.tensor([0, 1.25, 1.25, 0, 1.25, 1.25, 1.25, 0.0], device="cuda")
+    got = k.row_scale(dev(x, torch.bfloat16), s8, 49, dev(r, torch.bfloat16))
+    want = x * s8.cpu().repeat_interleave(49)[:, None] + r
+    close(got, want, torch.bfloat16, "row_scale")
+    close(k.row_scale(dev(x, torch.bfloat16), s8, 49), x * s8.cpu().repeat_interleave(49)[:, None], torch.bfloat16, "row_scale bwd")

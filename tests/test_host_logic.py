@@ -28,6 +28,7 @@ def build(cfg, dtype=torch.float32, device="cpu"):
     sd = synth.make_state_dict(geom, seed=cfg["weight_seed"])
     model = VALOR.from_pretrained(opts, sd)
     model.attach(dtype=dtype, device=device)
+    model.set_stochastic(False)          # parity mode: Dropout / DropPath disabled on both sides (see make_golden.py)
     batch = synth.make_batch(cfg["B"], cfg["F"], cfg["A"], cfg["T"], geom, seed=cfg["batch_seed"])
     tokens = batch["txt_tokens"]["bert_tokens"]
     ti, tl = synth.token_masker(tokens, 0.6, seed=cfg["mask_seed"])
@@ -82,8 +83,8 @@ def run_trajectory(model, batch, golden, loss_rtol, gn_rtol, param_rtol):
         assert abs(losses[k].item() - v) <= loss_rtol * abs(v), (k, losses[k].item(), v)
     named = dict(model.named_parameters())
     for k, ref in traj["params"].items():
-        assert abs(named[k].data.norm().item() - ref["norm"]) <= param_rtol * ref["norm"] + 1e-9, \
-            (k, named[k].data.norm().item(), ref["norm"])
+        assert abs(named[k].data.double().norm().item() - ref["norm"]) <= param_rtol * ref["norm"] + 1e-9, \
+            (k, named[k].data.double().norm().item(), ref["norm"])
 
 
 def test_state_dict_contract():
@@ -134,7 +135,7 @@ def test_forward_backward_matches_reference_golden(cpu_kernels, name):
         if ref is None:
             assert g.abs().sum().item() == 0.0, k
             continue
-        assert abs(g.norm().item() - ref["norm"]) <= 1e-3 * ref["norm"] + 1e-9, (k, g.norm().item(), ref["norm"])
+        assert abs(g.double().norm().item() - ref["norm"]) <= 1e-3 * ref["norm"] + 1e-9, (k, g.double().norm().item(), ref["norm"])
         torch.testing.assert_close(g.flatten()[:6], torch.tensor(ref["head"]), rtol=5e-3, atol=1e-6)
 
 
@@ -154,3 +155,38 @@ def test_evaluation_dict_matches_reference_logits(cpu_kernels):
         rows = len(ref["lse"])
         torch.testing.assert_close(sc[:rows, :8], torch.tensor(ref["head"]), rtol=3e-4, atol=3e-4)
     assert (ev["txt_labels_caption"] != -1).sum().item() == golden["logits"]["tva"]["n_rows"]
+
+
+def test_stochastic_mode_gradients_match_finite_differences(cpu_kernels):
+    """Dropout / DropPath wiring (functional.DropoutAddFn / DropPathAddFn): with the generator state pinned the masks
+    are a fixed function of the call site, so the hand-written backward must agree with central differences."""
+    golden = json.load(open(os.path.join(HERE, "golden", "golden_tiny.json")))
+    model, batch = build(golden["config"])
+    task = golden["config"]["task"]
+    model.set_stochastic(True, seed=3)
+
+    def loss():
+        model.rng._host[1] = 0            # same counter range -> same masks in every evaluation
+        out = model(batch, task, compute_loss=True)
+        return out, sum(out.values())
+
+    out, total = loss()
+    for k, v in golden["losses"].items():
+        assert abs(out[k].item() - v) > 1e-5 * abs(v)          # the masks are really applied
+    model.store.zero_grad()
+    total.backward()
+    named = dict(model.named_parameters())
+    probes = [("video_encoder.layers.2.blocks.1.mlp.fc2.bias", 5), ("audio_encoder.layer.1.attention.linears.3.bias", 9),
+              ("multimodal_encoder.encoder.layer.1.cross_attn.output.dense.bias", 17),
+              ("multimodal_encoder.embeddings.LayerNorm.bias", 3)]
+    for name, idx in probes:
+        p, g = named[name], named[name].main_grad.flatten()[idx].item()
+        eps = 5e-2
+        with torch.no_grad():
+            p.data.view(-1)[idx] += eps
+            lp = loss()[1].item()
+            p.data.view(-1)[idx] -= 2 * eps
+            lm = loss()[1].item()
+            p.data.view(-1)[idx] += eps
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - g) <= 3e-2 * max(abs(g), abs(fd)) + 1e-4, (name, fd, g)

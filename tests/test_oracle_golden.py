@@ -73,7 +73,7 @@ def test_oracle_matches_reference_golden(name):
         if ref is None:
             assert g is None or g.abs().sum().item() == 0.0, k
             continue
-        assert abs(g.norm().item() - ref["norm"]) <= 5e-4 * ref["norm"] + 1e-9, (k, g.norm().item(), ref["norm"])
+        assert abs(g.double().norm().item() - ref["norm"]) <= 5e-4 * ref["norm"] + 1e-9, (k, g.double().norm().item(), ref["norm"])
         torch.testing.assert_close(g.flatten()[:6], torch.tensor(ref["head"]), rtol=2e-3, atol=1e-7)
     unused = sorted(k for k, p in params.items() if p.grad is None)
     assert unused == golden["unused_params"], (unused, golden["unused_params"])
@@ -121,4 +121,4 @@ def test_oracle_optimizer_trajectory_matches_reference(name):
     for k, v in traj["final_losses"].items():
         assert abs(losses[k].item() - v) <= 2e-4 * abs(v), (k, losses[k].item(), v)
     for k, ref in traj["params"].items():
-        assert abs(params[k].norm().item() - ref["norm"]) <= 1e-5 * ref["norm"] + 1e-9, k
+        assert abs(params[k].double().norm().item() - ref["norm"]) <= 1e-5 * ref["norm"] + 1e-9, k

@@ -30,7 +30,7 @@ def report(name, dtype):
     for k, ref in golden["grads"].items():
         if ref is None:
             continue
-        out["grad_norm_rel_err"][k] = abs(named[k].main_grad.norm().item() - ref["norm"]) / (ref["norm"] + 1e-12)
+        out["grad_norm_rel_err"][k] = abs(named[k].main_grad.double().norm().item() - ref["norm"]) / (ref["norm"] + 1e-12)
     out["grad_norm_rel_err_max"] = max(out["grad_norm_rel_err"].values())
     got = masked_logits(model, golden)
     worst = 0.0
@@ -73,7 +73,7 @@ def report_torch_eager_bf16(name):
     for k, ref in golden["grads"].items():
         if ref is None or params[k].grad is None:
             continue
-        out["grad_norm_rel_err"][k] = abs(params[k].grad.norm().item() - ref["norm"]) / (ref["norm"] + 1e-12)
+        out["grad_norm_rel_err"][k] = abs(params[k].grad.double().norm().item() - ref["norm"]) / (ref["norm"] + 1e-12)
     out["grad_norm_rel_err_max"] = max(out["grad_norm_rel_err"].values())
     return out
 

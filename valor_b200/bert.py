@@ -128,15 +128,20 @@ class BertLayer(nn.Module):
         self.intermediate = _Intermediate(config)
         self.output = _Output(config)
         self.heads = config.num_attention_heads
+        self.hidden_dropout = config.hidden_dropout_prob       # bert.py:348,361,413
 
     def run(self, h, self_spec, media, cross_spec):
         """h [R*T, H]; media [B*S, H] or None.  (BertLayer.forward, bert.py:440-496)"""
         a = self.attention
         s = a.self
+        rng = getattr(self, "_rng", None) if self.training else None
+        pd = self.hidden_dropout
         qkv = Fn.linear(h, fused_lin([s.query.weight, s.key.weight, s.value.weight],
                                      [s.query.bias, s.key.bias, s.value.bias]))
         ctx = Fn.SelfAttnFn.apply(qkv, self_spec)
-        h = Fn.linear(ctx, lin_of(a.output.dense.weight, a.output.dense.bias), residual=h)
+        hin = h
+        h = Fn.residual_branch(lambda r: Fn.linear(ctx, lin_of(a.output.dense.weight, a.output.dense.bias), residual=r), hin,
+                               rng, pd)                                                # BertSelfOutput, bert.py:351-355
         h = Fn.layer_norm(h, LN(a.output.LayerNorm.weight, a.output.LayerNorm.bias, 1e-12))
         if media is not None:
             c = self.cross_attn
@@ -144,10 +149,14 @@ class BertLayer(nn.Module):
             q = Fn.linear(h, lin_of(x.query.weight, x.query.bias))
             kv = Fn.linear(media, fused_lin([x.key.weight, x.value.weight], [x.key.bias, x.value.bias]))
             ctx = Fn.CrossAttnFn.apply(q, kv, cross_spec)
-            h = Fn.linear(ctx, lin_of(c.output.dense.weight, c.output.dense.bias), residual=h)
+            hin = h
+            h = Fn.residual_branch(lambda r: Fn.linear(ctx, lin_of(c.output.dense.weight, c.output.dense.bias), residual=r),
+                                   hin, rng, pd)                                      # BertCrossOutput, bert.py:365-371
             h = Fn.layer_norm(h, LN(c.output.LayerNorm.weight, c.output.LayerNorm.bias, 1e-12))
-        h = Fn.mlp(h, lin_of(self.intermediate.dense.weight, self.intermediate.dense.bias),
-                   lin_of(self.output.dense.weight, self.output.dense.bias), K.ACT_GELU, residual=h)
+        hin = h
+        h = Fn.residual_branch(
+            lambda r: Fn.mlp(hin, lin_of(self.intermediate.dense.weight, self.intermediate.dense.bias),
+                             lin_of(self.output.dense.weight, self.output.dense.bias), K.ACT_GELU, residual=r), hin, rng, pd)
         return Fn.layer_norm(h, LN(self.output.LayerNorm.weight, self.output.LayerNorm.bias, 1e-12))
 
 
@@ -192,6 +201,9 @@ class BertModel(nn.Module):
                   "type": emb.token_type_embeddings.weight}
         h = Fn.BertEmbedFn.apply(anchor, tokens.contiguous(), tables, dtype)
         h = Fn.layer_norm(h, LN(emb.LayerNorm.weight, emb.LayerNorm.bias, 1e-12))
+        rng = getattr(self, "_rng", None) if self.training else None
+        if rng is not None and rng.active and cfg.hidden_dropout_prob > 0:
+            h = Fn.DropoutAddFn.apply(h, None, cfg.hidden_dropout_prob, rng)            # bert.py:217
         key_valid = (tokens != 0).to(torch.uint8).contiguous()
         n_pass = len(casual) if isinstance(casual, (list, tuple)) else 1
         cas = list(casual) if isinstance(casual, (list, tuple)) else [casual]

@@ -60,6 +60,9 @@ int grad_sumsq(const float*, long long, float*, cudaStream_t);
 int clip_coef(const float*, float, float*, cudaStream_t);
 int adamw(float*, const float*, float*, float*, void*, long long, const float*, const float*, cudaStream_t);
 int split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, cudaStream_t st);
+int dropout_apply(int, const void*, long long, const void*, long long, void*, long long, long long, int, float, const long long*, long long, cudaStream_t);
+int droppath_scale(float*, int, float, const long long*, long long, cudaStream_t);
+int row_scale(int, const void*, long long, const float*, long long, const void*, long long, void*, long long, long long, int, cudaStream_t);
 bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
                        const void* k, const void* v, const void* o);
 int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
@@ -299,6 +302,17 @@ int valor_cast2d(int src_dtype, int dst_dtype, const void* src, long long sld, v
 }
 int valor_split_bf16x3(const float* x, long long xld, void* out, long long R, long long C, int side, void* stream) {
   return split_bf16x3(x, xld, out, R, C, side, ST);
+}
+int valor_dropout(int dtype, const void* x, long long ldx, const void* residual, long long ldr, void* out, long long ldo, long long R,
+                  int C, float p, const long long* rng_state, long long site, void* stream) {
+  return dropout_apply(dtype, x, ldx, residual, ldr, out, ldo, R, C, p, rng_state, site, ST);
+}
+int valor_droppath_scale(float* scale, int B, float p, const long long* rng_state, long long site, void* stream) {
+  return droppath_scale(scale, B, p, rng_state, site, ST);
+}
+int valor_row_scale(int dtype, const void* x, long long ldx, const float* scale, long long rows_per_group, const void* residual,
+                    long long ldr, void* out, long long ldo, long long R, int C, void* stream) {
+  return row_scale(dtype, x, ldx, scale, rows_per_group, residual, ldr, out, ldo, R, C, ST);
 }
 int valor_act_bwd(int dtype, const void* dy, const void* h, void* dh, long long n, int act, void* stream) {
   return act_bwd(dtype, dy, h, dh, n, act, ST);

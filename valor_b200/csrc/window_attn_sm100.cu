@@ -422,11 +422,14 @@ window_fwd_sm100_kernel(FwdParams P) {
 //   [128,256) dP  = dO_qt . V_kt^T
 //   [256,384) dQ_qt accumulators (4 x 32 columns), live across the k-tiles
 //   [384,512) dK | dV accumulators of the current k-tile, double-buffered (2 x (32 + 32))
-// Element warps (one query row per thread): p = exp2(s*scale2 + bias2 - lse2), ds = p * (dP - delta); bf16 P and dS go
-// ONCE into 128-byte-swizzled [query][key] panels that serve  dV += P^T.dO  and  dK += dS^T.Q  as MN-major A operands and
-// dQ += dS.K as a K-major A operand; fp32 ds is folded into the warp's private slice of the bias-table gradient
-// (plain load / add / store: inside one key column the 32 queries of a warp hit distinct slots and a warp's shared-memory
-// instructions retire in order), the slices are merged per k-tile into a CTA table and sent to global memory once.
+// Sixteen element warps (tensor-memory lane quarter x 32-key column group), one query row per thread:
+// p = exp2(s*scale2 + bias2 - lse2), ds = p * (dP - delta); bf16 P and dS go ONCE into 128-byte-swizzled [query][key]
+// panels that serve  dV += P^T.dO  and  dK += dS^T.Q  as MN-major A operands and  dQ += dS.K  as a K-major A operand.
+// Bias-table gradient: fp32 ds is folded into the warp's private slice (plain load / add / store: inside one key
+// column the 32 queries of a warp hit distinct slots and a warp's shared-memory instructions retire in order); a
+// slice only spans (32 queries + 32 keys) of relative-position codes, is double-buffered, and is merged into the CTA
+// table by all element threads while the next block is already being processed; the CTA table goes to global memory
+// once per (window, head).
 struct BwdParams {
   const bf16* qkv; long long ld;
   const bf16* O; const bf16* dO; long long ldo;
@@ -437,9 +440,12 @@ struct BwdParams {
   int heads;
   int nqt, nkt;
   int n_used, maxcode, center;
-  int gt_bytes;                    // bytes of one element warp's private gradient slice
+  int gt_bytes;                    // size of one private gradient slice (see bwd_gt_bytes)
   WindowIndex win;
 };
+
+constexpr int NEW = 16;            // element warps
+constexpr int NET = NEW * 32;      // element threads
 
 struct BwdSmem {
   unsigned char *Qs, *dOs, *Ks, *Vs, *Pb, *dSb;
@@ -447,7 +453,8 @@ struct BwdSmem {
   float* tab2;
   float* ld2;           // [512][2]: lse * log2e (+inf on padding rows), -delta
   float* ctab;          // CTA-level bias-table gradient [n_used]
-  unsigned char* gpriv; // 8 private slices
+  unsigned char* gpriv; // [2 buffers][16 warps][gt_bytes]
+  int* winfo;           // [2 buffers][8]: qlo[4] (first query code word of each lane quarter), khi[4] (last key code word of each column group)
   uint64_t* bars;
   uint32_t* tmem_slot;
 };
@@ -461,7 +468,8 @@ static inline size_t bwd_smem_bytes(int nqt, int n_used, int gt_bytes, bool want
   const size_t tabb = ((size_t)n_used * 4 + 15) / 16 * 16;
   b += tabb;
   b += 512 * 2 * 4;
-  if (want_dtab) b += tabb + (size_t)8 * gt_bytes;
+  if (want_dtab) b += tabb + (size_t)2 * NEW * gt_bytes;
+  b += 2 * 8 * 4;
   b += 16 * 8 + 16;
   return b;
 }
@@ -486,8 +494,9 @@ __device__ __forceinline__ BwdSmem bwd_carve(unsigned char* raw, const BwdParams
   unsigned char* nxt = (unsigned char*)(S.ld2 + 1024);
   S.ctab = (float*)nxt;
   S.gpriv = nxt + tabb;
-  if (P.dtable != nullptr) nxt = S.gpriv + (size_t)8 * P.gt_bytes;
-  S.bars = (uint64_t*)nxt;
+  if (P.dtable != nullptr) nxt = S.gpriv + (size_t)2 * NEW * P.gt_bytes;
+  S.winfo = (int*)nxt;
+  S.bars = (uint64_t*)(S.winfo + 16);
   S.tmem_slot = (uint32_t*)(S.bars + 16);
   return S;
 }
@@ -499,12 +508,52 @@ __device__ __forceinline__ void stv_f32(uint32_t a, float v) { asm volatile("st.
 // barrier slots
 enum { B_SFULL = 0, B_SFREE = 2, B_PDFULL = 4, B_PDFREE = 5, B_KVFULL = 6, B_KVLOAD = 8, B_QFULL = 9 };
 
+// 16 key columns of one query row: probabilities, dS, bias-gradient fold, bf16 packing.  TAIL: only the first `nv`
+// columns hold real keys (the others produce zeros and are not folded).
+template <bool MASKED, bool TAIL>
+__device__ __forceinline__ void bwd_cols16(const uint32_t* sv, const uint32_t* dv, uint32_t kc_s, uint32_t kr_s, int kg, int nv,
+                                           uint32_t qaddr, uint32_t gaddr, uint32_t qrg, float scale2, float l2, float nd,
+                                           bool want_dtab, uint32_t* pw, uint32_t* dw) {
+  const float kMask2 = -100.0f * kLog2e;
+  uint32_t kc[16], kr[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 t = lds_v4(kc_s + (kg + g * 4) * 4);
+    kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
+    if (MASKED) {
+      const uint4 u = lds_v4(kr_s + (kg + g * 4) * 4);
+      kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
+    }
+  }
+  float pf[16], df[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = fmaf(__uint_as_float(sv[j]), scale2, lds_f32(qaddr - kc[j]));
+    if (MASKED && qrg != kr[j]) x += kMask2;
+    float pr = ex2f(x - l2);                   // l2 = +inf on padding queries -> 0
+    if (TAIL && j >= nv) pr = 0.f;             // padding key (warp-uniform)
+    pf[j] = pr;
+    df[j] = pr * (__uint_as_float(dv[j]) + nd);
+  }
+  if (want_dtab) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (!TAIL || j < nv) {
+        const uint32_t slot = gaddr - kc[j];
+        stv_f32(slot, ldv_f32(slot) + df[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]); dw[j] = pack_bf16(df[2 * j], df[2 * j + 1]); }
+}
+
 template <bool MASKED>
 __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdSmem& S, int h, uint32_t tmem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = warp - 4;
-  const int qtr = e & 3, half = e >> 2;
-  const int et = threadIdx.x - 128;                 // 0..255 among the element threads
+  const int qtr = e & 3, grp = e >> 2, half = grp >> 1;   // lane quarter (hardware: warp % 4), 32-key column group, S/dP half
+  const int et = threadIdx.x - 128;                       // 0..511 among the element threads
   const int N = P.win.N;
   const int C = P.heads * HD;
   const uint32_t lane_t = tmem + ((uint32_t)(qtr * 32) << 16);
@@ -512,108 +561,110 @@ __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdS
   const uint32_t tab_s = s_u32(S.tab2), kc_s = s_u32(S.kcode), kr_s = s_u32(S.qreg);
   const int rloc = qtr * 32 + lane;
   const bool want_dtab = P.dtable != nullptr;
-  const uint32_t gt_s = s_u32(S.gpriv) + (uint32_t)(e * P.gt_bytes);
-  const float kMask2 = -100.0f * kLog2e;
   const uint32_t pb_s = s_u32(S.Pb) + half * 16384 + rloc * 128, dsb_s = s_u32(S.dSb) + half * 16384 + rloc * 128;
   const int sw = rloc & 7;
+  const int cbase = (grp & 1) * 4;                        // first 16-byte chunk of this group inside the 64-key panel row
+  // merge of a block's private slices into the CTA table (runs while the MMAs of that block are in flight)
+  auto flush = [&](int b) {
+    const int kt = b / P.nqt, qt = b % P.nqt;
+    const int* wi = S.winfo + (b & 1) * 8;
+    int qlo[4], khi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qlo[i] = wi[i]; khi[i] = wi[4 + i]; }
+    const int ulo = (int)S.qcode[qt * 128] - (int)S.kcode[min(kt * 128 + 127, N - 1)];
+    const int uhi = (int)S.qcode[min(qt * 128 + 127, N - 1)] - (int)S.kcode[kt * 128];
+    const uint32_t gp = s_u32(S.gpriv) + (uint32_t)((b & 1) * NEW * P.gt_bytes);
+    for (int sb = ulo + 4 * et; sb <= uhi; sb += 4 * NET) {
+      float acc = 0.f;
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) {
+        const int d = sb - qlo[qi];
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const uint32_t off = (uint32_t)(d + khi[gi]);      // negative -> huge -> fails the unsigned range test
+          if (off < (uint32_t)P.gt_bytes) {
+            const uint32_t a = gp + (uint32_t)((gi * 4 + qi) * P.gt_bytes) + off;
+            acc += ldv_f32(a);
+            stv_f32(a, 0.f);
+          }
+        }
+      }
+      S.ctab[sb >> 2] += acc;
+    }
+  };
   for (int kt = 0; kt < P.nkt; ++kt) {
-    // key range of this warp's column half: codes grow with the token index
-    const int k_first = kt * 128 + half * 64;
-    const int k_last = min(k_first + 63, N - 1);
-    const bool has_keys = k_first < N;
-    const int kc_hi = has_keys ? (int)S.kcode[k_last] : 0;
-    const int lo_b = 4 * P.maxcode - kc_hi;           // smallest slot byte offset this warp can touch in this k-tile
+    const int k0 = kt * 128 + grp * 32;                   // first key of this warp's column group
+    const int nvk = min(32, N - k0);                      // real keys in the group (<= 0: none)
+    const int kc_hi = nvk > 0 ? (int)S.kcode[k0 + nvk - 1] : 0;
     for (int qt = 0; qt < P.nqt; ++qt) {
       const int b = kt * P.nqt + qt;
-      const int q = qt * 128 + rloc;
-      const bool live = has_keys && (qt * 128 + qtr * 32) < N;
-      const uint32_t qcode = S.qcode[q];
+      const int q0 = qt * 128 + qtr * 32;
+      const int q = q0 + lane;
+      const bool live = nvk > 0 && q0 < N;
+      const uint32_t qcode = S.qcode[min(q, N - 1)];        // padding lanes fold zeros into a valid slot
+      const int qc0 = (int)S.qcode[min(q0, N - 1)];
+      const int lo_b = qc0 - kc_hi;                        // smallest slot byte offset this warp touches in this block
       const uint32_t qaddr = tab_s + qcode;
-      const uint32_t gaddr = gt_s + qcode - (uint32_t)lo_b;
-      const uint32_t qrg = S.qreg[q];
+      const uint32_t gaddr = s_u32(S.gpriv) + (uint32_t)(((b & 1) * NEW + e) * P.gt_bytes) + qcode - (uint32_t)lo_b;
+      const uint32_t qrg = S.qreg[min(q, N - 1)];
       const float l2 = S.ld2[2 * q], nd = S.ld2[2 * q + 1];
+      if (want_dtab && lane == 0) {                       // this block's slice origins (same value from every warp of a row / column)
+        if (grp == 0) S.winfo[(b & 1) * 8 + qtr] = q0 < N ? qc0 : (1 << 28);
+        if (qtr == 0) S.winfo[(b & 1) * 8 + 4 + grp] = nvk > 0 ? kc_hi : -(1 << 28);
+      }
       bar_wait(&bars[B_SFULL + half], b & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int sub = 0; sub < 4; ++sub) {
-        const int c0 = half * 64 + sub * 16;
-        const int kg = kt * 128 + c0;
-        uint32_t pw[8], dw[8];
-        if (live && kg < N) {
+      uint32_t pw[2][8], dw[2][8];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = grp * 32 + sub * 16;               // column inside the 128-key block
+        const int nv = nvk - sub * 16;                    // real keys among these 16 columns
+        if (live && nv > 0) {
           uint32_t sv[16], dv[16];
           VALOR_TMEM_LD16(lane_t + TB_S + c0, sv);
           VALOR_TMEM_LD16(lane_t + TB_DP + c0, dv);
-          uint32_t kc[16], kr[16];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint4 t = lds_v4(kc_s + (kg + g * 4) * 4);
-            kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
-            if (MASKED) {
-              const uint4 u = lds_v4(kr_s + (kg + g * 4) * 4);
-              kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
-            }
-          }
           tmem_wait_ld();
-          if (sub == 3) {   // every tensor-memory read of this block's half is in registers: hand S / dP back to the MMAs
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
-          }
-          float pf[16], df[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = fmaf(__uint_as_float(sv[j]), P.scale2, lds_f32(qaddr - kc[j]));
-            if (MASKED && qrg != kr[j]) x += kMask2;
-            float pr = ex2f(x - l2);                   // l2 = +inf on padding queries -> 0
-            if (kg + j >= N) pr = 0.f;                 // padding key (warp-uniform)
-            pf[j] = pr;
-            df[j] = pr * (__uint_as_float(dv[j]) + nd);
-          }
-          if (want_dtab) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (kg + j < N) {
-                const uint32_t slot = gaddr - kc[j];
-                stv_f32(slot, ldv_f32(slot) + df[j]);
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]); dw[j] = pack_bf16(df[2 * j], df[2 * j + 1]); }
+          if (nv >= 16) bwd_cols16<MASKED, false>(sv, dv, kc_s, kr_s, kt * 128 + c0, 16, qaddr, gaddr, qrg, P.scale2, l2, nd, want_dtab, pw[sub], dw[sub]);
+          else bwd_cols16<MASKED, true>(sv, dv, kc_s, kr_s, kt * 128 + c0, nv, qaddr, gaddr, qrg, P.scale2, l2, nd, want_dtab, pw[sub], dw[sub]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pw[j] = dw[j] = 0u;
-          if (sub == 3) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
-          }
+          for (int j = 0; j < 8; ++j) pw[sub][j] = dw[sub][j] = 0u;
         }
-        if (sub == 0 && b > 0) bar_wait(&bars[B_PDFREE], (b - 1) & 1);   // the previous block's dV / dK / dQ MMAs have read the panels
-        const uint32_t o0 = (uint32_t)(((sub * 2) ^ sw) << 4), o1 = (uint32_t)(((sub * 2 + 1) ^ sw) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o0), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o1), "r"(pw[4]), "r"(pw[5]), "r"(pw[6]), "r"(pw[7]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o0), "r"(dw[0]), "r"(dw[1]), "r"(dw[2]), "r"(dw[3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o1), "r"(dw[4]), "r"(dw[5]), "r"(dw[6]), "r"(dw[7]) : "memory");
+      }
+      tc_fence_before();                                  // every tensor-memory read of this block is in registers
+      __syncwarp();
+      if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
+      if (b > 0) bar_wait(&bars[B_PDFREE], (b - 1) & 1);  // the previous block's dV / dK / dQ MMAs have read the panels
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t o0 = (uint32_t)(((cbase + sub * 2) ^ sw) << 4), o1 = (uint32_t)(((cbase + sub * 2 + 1) ^ sw) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o0), "r"(pw[sub][0]), "r"(pw[sub][1]), "r"(pw[sub][2]), "r"(pw[sub][3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o1), "r"(pw[sub][4]), "r"(pw[sub][5]), "r"(pw[sub][6]), "r"(pw[sub][7]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o0), "r"(dw[sub][0]), "r"(dw[sub][1]), "r"(dw[sub][2]), "r"(dw[sub][3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o1), "r"(dw[sub][4]), "r"(dw[sub][5]), "r"(dw[sub][6]), "r"(dw[sub][7]) : "memory");
       }
       proxy_fence();
       __syncwarp();
       if (lane == 0) bar_arrive(&bars[B_PDFULL]);
+      if (want_dtab) {
+        named_bar(5, NET);                                // every element warp has finished this block's folds
+        flush(b);
+      }
     }
-    // ---------------- k-tile epilogue: dK (half 0 warps) / dV (half 1 warps) rows of this tile
+    // ---------------- k-tile epilogue: dK (column groups 0,1) / dV (groups 2,3) rows of this tile, 16 channels per warp
     bar_wait(&bars[B_KVFULL + (kt & 1)], (kt >> 1) & 1);
     tc_fence_after();
     {
       const int key = kt * 128 + rloc;
       if (kt * 128 + qtr * 32 < N) {
-        uint32_t a[32];
-        VALOR_TMEM_LD32(lane_t + TB_DKV + (kt & 1) * 64 + half * 32, a);
+        uint32_t a[16];
+        VALOR_TMEM_LD16(lane_t + TB_DKV + (kt & 1) * 64 + half * 32 + (grp & 1) * 16, a);
         tmem_wait_ld();
         if (key < N) {
           const float mul = half == 0 ? P.scale : 1.0f;
-          bf16* dst = P.dqkv + (size_t)S.qrow[key] * P.lddqkv + (half == 0 ? C : 2 * C) + h * HD;
+          bf16* dst = P.dqkv + (size_t)S.qrow[key] * P.lddqkv + (half == 0 ? C : 2 * C) + h * HD + (grp & 1) * 16;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             uint4 w;
             w.x = pack_bf16(__uint_as_float(a[g * 8 + 0]) * mul, __uint_as_float(a[g * 8 + 1]) * mul);
             w.y = pack_bf16(__uint_as_float(a[g * 8 + 2]) * mul, __uint_as_float(a[g * 8 + 3]) * mul);
@@ -625,69 +676,41 @@ __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdS
       }
       tc_fence_before();
     }
-    // ---------------- merge the private gradient slices of this k-tile into the CTA table
-    if (want_dtab) {
-      named_bar(5, 256);
-      // slice of warp w: slot byte offsets [lo(w), lo(w) + gt_bytes); lo depends on the warp's key half only
-      int lo[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int kf = kt * 128 + c * 64;
-        lo[c] = kf < N ? 4 * P.maxcode - (int)S.kcode[min(kf + 63, N - 1)] : (1 << 30);
-      }
-      const uint32_t gp = s_u32(S.gpriv);
-      for (int sb = 4 * et; sb < 4 * P.n_used; sb += 4 * 256) {
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const int off = sb - lo[w >> 2];
-          if (off >= 0 && off < P.gt_bytes) {
-            const uint32_t a = gp + (uint32_t)(w * P.gt_bytes + off);
-            acc += ldv_f32(a);
-            stv_f32(a, 0.f);
-          }
-        }
-        S.ctab[sb >> 2] += acc;
-      }
-      named_bar(5, 256);
-    }
   }
-  // ---------------- dQ: every k-tile has been accumulated
+  // ---------------- dQ: every k-tile has been accumulated; 8 channels per warp
   bar_wait(&bars[B_QFULL], 0);
   tc_fence_after();
   for (int qt = 0; qt < P.nqt; ++qt) {
     const int q = qt * 128 + rloc;
     if (qt * 128 + qtr * 32 < N) {
-      uint32_t a[16];
-      VALOR_TMEM_LD16(lane_t + TB_DQ + qt * 32 + half * 16, a);
+      uint32_t a[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+                   : "r"(lane_t + TB_DQ + qt * 32 + grp * 8));
       tmem_wait_ld();
       if (q < N) {
-        bf16* dst = P.dqkv + (size_t)S.qrow[q] * P.lddqkv + h * HD + half * 16;
-        uint4 w0, w1;
+        bf16* dst = P.dqkv + (size_t)S.qrow[q] * P.lddqkv + h * HD + grp * 8;
+        uint4 w0;
         w0.x = pack_bf16(__uint_as_float(a[0]) * P.scale, __uint_as_float(a[1]) * P.scale);
         w0.y = pack_bf16(__uint_as_float(a[2]) * P.scale, __uint_as_float(a[3]) * P.scale);
         w0.z = pack_bf16(__uint_as_float(a[4]) * P.scale, __uint_as_float(a[5]) * P.scale);
         w0.w = pack_bf16(__uint_as_float(a[6]) * P.scale, __uint_as_float(a[7]) * P.scale);
-        w1.x = pack_bf16(__uint_as_float(a[8]) * P.scale, __uint_as_float(a[9]) * P.scale);
-        w1.y = pack_bf16(__uint_as_float(a[10]) * P.scale, __uint_as_float(a[11]) * P.scale);
-        w1.z = pack_bf16(__uint_as_float(a[12]) * P.scale, __uint_as_float(a[13]) * P.scale);
-        w1.w = pack_bf16(__uint_as_float(a[14]) * P.scale, __uint_as_float(a[15]) * P.scale);
         *(uint4*)dst = w0;
-        *(uint4*)(dst + 8) = w1;
       }
     }
   }
   tc_fence_before();
   if (want_dtab) {
+    named_bar(5, NET);                                    // the last block's merge is complete
     const int r0 = P.center - P.maxcode;
-    for (int r = et; r < P.n_used; r += 256) {
+    for (int r = et; r < P.n_used; r += NET) {
       const float v = S.ctab[r];
       if (v != 0.f) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], v);
     }
   }
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(128 + NET, 1)
 window_bwd_sm100_kernel(BwdParams P) {
   extern __shared__ unsigned char smem_raw[];
   const BwdSmem S = bwd_carve(smem_raw, P);
@@ -698,8 +721,8 @@ window_bwd_sm100_kernel(BwdParams P) {
   uint64_t* bars = S.bars;
   if (threadIdx.x == 0) {
     bar_init(&bars[B_SFULL], 1); bar_init(&bars[B_SFULL + 1], 1);
-    bar_init(&bars[B_SFREE], 4); bar_init(&bars[B_SFREE + 1], 4);
-    bar_init(&bars[B_PDFULL], 8); bar_init(&bars[B_PDFREE], 1);
+    bar_init(&bars[B_SFREE], NEW / 2); bar_init(&bars[B_SFREE + 1], NEW / 2);
+    bar_init(&bars[B_PDFULL], NEW); bar_init(&bars[B_PDFREE], 1);
     bar_init(&bars[B_KVFULL], 1); bar_init(&bars[B_KVFULL + 1], 1);
     bar_init(&bars[B_KVLOAD], 64); bar_init(&bars[B_QFULL], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -711,7 +734,7 @@ window_bwd_sm100_kernel(BwdParams P) {
   const bool masked = build_tables(P.win, P.maxcode, P.center, P.n_used, p, h, S.qrow, S.qcode, S.kcode, S.qreg, S.tab2, 512);
   if (P.dtable != nullptr) {
     float* z = S.ctab;
-    const int nz = (int)(((size_t)P.n_used * 4 + 15) / 16 * 4) + 8 * P.gt_bytes / 4;   // CTA table + private slices (contiguous)
+    const int nz = (int)(((size_t)P.n_used * 4 + 15) / 16 * 4) + 2 * NEW * P.gt_bytes / 4;   // CTA table + private slices (contiguous)
     for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0.f;
   }
   __syncthreads();
@@ -867,13 +890,15 @@ int window_sm100_fwd(const WindowIndex& ix, const void* qkv, long long ld, void*
   return check_launch("window_fwd_sm100_kernel");
 }
 
-// bytes of one element warp's private gradient slice: 4 * (maxcode + widest code span of an aligned 64-token range + 1)
+// bytes of one element warp's private gradient slice: a block's slots for 32 consecutive queries x 32 consecutive keys
+// span  2 * (widest code span of an aligned 32-token range) + 1  relative-position codes
 static int bwd_gt_bytes(const WindowIndex& ix, int maxcode) {
+  (void)maxcode;
   const int cW = 2 * ix.WW - 1, cH = (2 * ix.WH - 1) * cW;
   auto code = [&](int i) { return (i / (ix.wh * ix.ww)) * cH + ((i / ix.ww) % ix.wh) * cW + i % ix.ww; };
   int span = 0;
-  for (int f = 0; f < ix.N; f += 64) span = std::max(span, code(std::min(f + 63, ix.N - 1)) - code(f));
-  return (4 * (maxcode + span + 1) + 15) / 16 * 16;
+  for (int f = 0; f < ix.N; f += 32) span = std::max(span, code(std::min(f + 31, ix.N - 1)) - code(f));
+  return (4 * (2 * span + 1) + 15) / 16 * 16;
 }
 
 bool window_sm100_bwd_eligible(const WindowIndex& ix, int hd, bool want_dtab) {
@@ -898,7 +923,7 @@ int window_sm100_bwd(const WindowIndex& ix, const void* qkv, long long ld, const
   const size_t smem = bwd_smem_bytes(P.nqt, P.n_used, P.gt_bytes, dtable != nullptr);
   static size_t attr = 0;
   if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  window_bwd_sm100_kernel<<<dim3(Pn, H), 384, smem, st>>>(P);
+  window_bwd_sm100_kernel<<<dim3(Pn, H), 128 + NET, smem, st>>>(P);
   return check_launch("window_bwd_sm100_kernel");
 }
 

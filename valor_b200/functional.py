@@ -378,6 +378,79 @@ class L2NormFn(Function):
         return K.l2norm_bwd(dy, x, nrm)
 
 
+class RngState:
+    """{seed, step offset} in device memory + the host-side call-site counter of the current step.  Every stochastic
+    layer takes the next site id in forward order and keeps it for its backward; `begin_step` advances the device
+    offset (16-byte copy), so a captured CUDA graph replays with new masks."""
+    STRIDE = 1 << 24
+
+    def __init__(self, device, seed=0):
+        self.state = torch.tensor([int(seed), 0], dtype=torch.int64, device=device)
+        self._host = torch.tensor([int(seed), 0], dtype=torch.int64)
+        self.site = 0
+        self.active = True
+
+    def begin_step(self):
+        """start of a forward pass: restart the call-site numbering and move to a fresh counter range.  While a CUDA
+        graph is being captured only the numbering restarts: the replaying loop calls `advance()` itself."""
+        self.site = 0
+        if not (self.state.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.advance()
+
+    def advance(self):
+        self._host[1] += self.STRIDE
+        self.state.copy_(self._host, non_blocking=True)
+
+    def next_site(self):
+        self.site += 1
+        return self.site
+
+
+class DropoutAddFn(Function):
+    """out = residual + dropout(x, p): nn.Dropout before the residual add of BERT / AST sub-layers
+    (bert.py:353-355,367-371,418-420; transformer.py:78,83) and on embeddings (residual None)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, rng):
+        ctx.p, ctx.rng, ctx.site, ctx.has_res = p, rng, rng.next_site(), residual is not None
+        return K.dropout(x.contiguous(), None if residual is None else residual.contiguous(), p, rng.state, ctx.site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        return K.dropout(dy, None, ctx.p, ctx.rng.state, ctx.site), (dy if ctx.has_res else None), None, None
+
+
+class DropPathAddFn(Function):
+    """out = shortcut + drop_path(branch): per-sample keep mask / keep_prob (videoswin.py:40-55,238,243)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, n_groups, rng):
+        site = rng.next_site()
+        scale = K.droppath_scale(n_groups, p, rng.state, site)
+        ctx.save_for_backward(scale)
+        ctx.rpg = x.shape[0] // n_groups
+        return K.row_scale(x.contiguous(), scale, ctx.rpg, residual.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        return K.row_scale(dy, scale, ctx.rpg), dy, None, None, None
+
+
+def residual_branch(y_fn, residual, rng, p, n_groups=None):
+    """x + regularise(branch): `y_fn(res)` runs the branch's last GEMM with `res` fused into its epilogue.  Without an
+    active generator (eval / parity mode, or p == 0) the residual add stays fused; otherwise the GEMM runs bare and
+    Dropout (n_groups None) or DropPath (n_groups = batch) is applied together with the add."""
+    if rng is None or not rng.active or p <= 0.0:
+        return y_fn(residual)
+    y = y_fn(None)
+    if n_groups is None:
+        return DropoutAddFn.apply(y, residual, p, rng)
+    return DropPathAddFn.apply(y, residual, p, n_groups, rng)
+
+
 class CastFn(Function):
     """dtype change between the fp32 contrastive head and the low-precision GEMM operands"""
 

@@ -296,6 +296,30 @@ def split_bf16x3(x, side):
     return out
 
 
+def dropout(x, residual, p, rng_state, site, out=None):
+    """out = residual + x * keep / (1-p)  (residual None: plain dropout); mask = f(rng_state, site, element index)"""
+    R, C = x.shape
+    out = torch.empty(R, C, device=x.device, dtype=x.dtype) if out is None else out
+    _call("valor_dropout", DT(x), P(x), _ld(x), P(residual), _ld(residual) if residual is not None else 0, P(out), _ld(out), R, C,
+          float(p), P(rng_state), int(site), ST())
+    return out
+
+
+def droppath_scale(B, p, rng_state, site):
+    scale = torch.empty(B, device=rng_state.device, dtype=torch.float32)
+    _call("valor_droppath_scale", P(scale), B, float(p), P(rng_state), int(site), ST())
+    return scale
+
+
+def row_scale(x, scale, rows_per_group, residual=None):
+    """out[r] = residual[r] + x[r] * scale[r // rows_per_group]"""
+    R, C = x.shape
+    out = torch.empty(R, C, device=x.device, dtype=x.dtype)
+    _call("valor_row_scale", DT(x), P(x), _ld(x), P(scale), int(rows_per_group), P(residual),
+          _ld(residual) if residual is not None else 0, P(out), _ld(out), R, C, ST())
+    return out
+
+
 def act_bwd(dy, h, act):
     dy = dy.contiguous()
     dh = torch.empty_like(h)

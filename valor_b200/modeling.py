@@ -172,7 +172,20 @@ class VALORModel(nn.Module):
         self.to(device)
         self.store = ParamStore(self, dtype=dtype, device=torch.device(device))
         self.compute_dtype = dtype
+        # stochastic regularisation (Dropout 0.1 in BERT / AST, DropPath 0 -> 0.2 in VideoSwin) is ON in train() mode like
+        # the reference's nn.Dropout / DropPath modules; `set_stochastic(False)` is the parity mode of the tests (both
+        # sides disabled: the reference draws its masks from torch's host-seeded generator, not reproducible here)
+        self.rng = Fn.RngState(torch.device(device), seed=getattr(self.config, "seed", 0))
+        for m in self.modules():
+            m._rng = self.rng
         return self.store
+
+    def set_stochastic(self, on=True, seed=None):
+        self.rng.active = bool(on)
+        if seed is not None:
+            self.rng._host[0] = int(seed)
+            self.rng.state.copy_(self.rng._host)
+        return self
 
     # ---- encoder wiring (token-matrix forms of modeling.py:449-502) -------------------------
     def forward_video_encoder(self, video_pixels):

@@ -54,6 +54,8 @@ class VALOR(VALORModel):
                 if task not in cache:
                     cache[task] = self.unused_parameter_names(task)
                 self.store.set_unused(cache[task])
+            if self.store is not None and self.training and self.rng.active:
+                self.rng.begin_step()     # new masks every forward (also under CUDA-graph replay: see RngState)
             return self.forward_pt(batch, task, compute_loss=compute_loss)
         raise NotImplementedError("ret/cap/qa heads are the next §8 rows (SURVEY.md §8f N1-N3)")
 

@@ -38,20 +38,25 @@ class TransformerLayer(nn.Module):
         self.layernorm1 = _Norm(config.hidden_size, eps=1e-12)
         self.layernorm2 = _Norm(config.hidden_size, eps=1e-12)
         self.mode = mode
+        self.hidden_dropout = config.hidden_dropout            # nn.Dropout(config.hidden_dropout), transformer.py:61
+        self.attention_dropout = config.attention_dropout      # transformer.py:112 (applied by the attention kernel)
 
     def run(self, x, n_seq, seq_len):
         att = self.attention
+        rng = getattr(self, "_rng", None) if self.training else None
         H = att.head_num
         hd = att.hidden_size // H
         h, xr = Fn.layer_norm_residual(x, LN(self.layernorm1.weight, self.layernorm1.bias, 1e-12))
         qkv = Fn.linear(h, fused_lin([l.weight for l in att.linears[:3]], [l.bias for l in att.linears[:3]]))
         spec = dict(P=n_seq, H=H, hd=hd, Nq=seq_len, max_nk=seq_len, scale=1.0 / math.sqrt(hd))
         o = Fn.SelfAttnFn.apply(qkv, spec)
-        x = Fn.linear(o, lin_of(att.linears[3].weight, att.linears[3].bias), residual=xr)
+        x = Fn.residual_branch(lambda r: Fn.linear(o, lin_of(att.linears[3].weight, att.linears[3].bias), residual=r), xr, rng,
+                               self.hidden_dropout)                                    # residual + dropout(attn), :78
         h, xr = Fn.layer_norm_residual(x, LN(self.layernorm2.weight, self.layernorm2.bias, 1e-12))
         ff = self.ff_layer
-        return Fn.mlp(h, lin_of(ff.linear1.weight, ff.linear1.bias), lin_of(ff.linear2.weight, ff.linear2.bias),
-                      K.ACT_GELU, residual=xr)
+        return Fn.residual_branch(
+            lambda r: Fn.mlp(h, lin_of(ff.linear1.weight, ff.linear1.bias), lin_of(ff.linear2.weight, ff.linear2.bias),
+                             K.ACT_GELU, residual=r), xr, rng, self.hidden_dropout)   # residual + dropout(ff), :83
 
 
 class TransformerEncoder(nn.Module):
@@ -86,6 +91,7 @@ class AudioEmbeddings(nn.Module):
         self.position_embeddings = nn.Module()
         self.position_embeddings.weight = nn.Parameter(torch.empty(self.token_length_per_frame + 1, H).normal_(0, 0.02))
         self.cls_token = nn.Parameter(0.02 * torch.randn(1, 1, H))
+        self.hidden_dropout = model_cfg_audio.hidden_dropout   # modeling.py:748,761
         self.register_buffer("_anchor", torch.zeros(1), persistent=False)
 
     def run(self, spec, dtype):
@@ -97,4 +103,8 @@ class AudioEmbeddings(nn.Module):
         lin = Fn.Lin(w.lp.view(H, -1), w.main_grad.view(H, -1), self.first_conv.bias.data, self.first_conv.bias.main_grad)
         anchor = self._anchor.requires_grad_(True) if torch.is_grad_enabled() else None
         tok = Fn.linear(cols, lin, anchor=anchor)
-        return Fn.AstAssembleFn.apply(tok, self.cls_token, self.position_embeddings.weight, N, self.token_length_per_frame)
+        x = Fn.AstAssembleFn.apply(tok, self.cls_token, self.position_embeddings.weight, N, self.token_length_per_frame)
+        rng = getattr(self, "_rng", None) if self.training else None
+        if rng is not None and rng.active and self.hidden_dropout > 0:
+            x = Fn.DropoutAddFn.apply(x, None, self.hidden_dropout, rng)              # modeling.py:761
+        return x

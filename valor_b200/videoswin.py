@@ -101,13 +101,16 @@ class SwinTransformerBlock3D(nn.Module):
         hd = self.dim // self.num_heads
         geom = (grid, ws, ss, tuple(self.window_size), self.num_heads, hd, self.attn.scale)
         a = self.attn
+        rng = getattr(self, "_rng", None) if self.training else None     # DropPath (videoswin.py:238,243): training only
+        dp = self.drop_path_rate
         y, xr = Fn.layer_norm_residual(x, LN(self.norm1.weight, self.norm1.bias, self.norm1.eps))
         qkv = Fn.linear(y, lin_of(a.qkv.weight, a.qkv.bias))
         o = Fn.window_attention(qkv, a.relative_position_bias_table, geom)
-        x = Fn.linear(o, lin_of(a.proj.weight, a.proj.bias), residual=xr)
+        x = Fn.residual_branch(lambda r: Fn.linear(o, lin_of(a.proj.weight, a.proj.bias), residual=r), xr, rng, dp, B)
         y, xr = Fn.layer_norm_residual(x, LN(self.norm2.weight, self.norm2.bias, self.norm2.eps))
-        return Fn.mlp(y, lin_of(self.mlp.fc1.weight, self.mlp.fc1.bias), lin_of(self.mlp.fc2.weight, self.mlp.fc2.bias),
-                      K.ACT_GELU, residual=xr)
+        return Fn.residual_branch(
+            lambda r: Fn.mlp(y, lin_of(self.mlp.fc1.weight, self.mlp.fc1.bias), lin_of(self.mlp.fc2.weight, self.mlp.fc2.bias),
+                             K.ACT_GELU, residual=r), xr, rng, dp, B)
 
 
 class PatchMerging(nn.Module):
