@@ -182,6 +182,12 @@ int valor_fine_reduce_bwd(const float* L, long long ldl, const unsigned char* mA
 int valor_contrastive_fwd(const float* S, const float* temp, float* row_lse, float* col_lse, float* loss, int N, void* stream);
 int valor_contrastive_bwd(const float* S, const float* temp, const float* row_lse, const float* col_lse, const float* gptr, float gmul, float* dS, float* dtemp, int N, void* stream);
 
+/* ---- retrieval evaluation (test.py:680-775): rank of the ground-truth candidate of every query = number of candidates with a
+ * higher score (replaces sort + host list.index); strides select the direction (text->video: rows, video->text: columns).
+ * valor_dual_softmax: S * softmax(S / temp, over the `norm` direction) * Nnorm (compute_dualsoftmax_forward/backward). */
+int valor_retrieval_rank(const float* S, long long stride_query, long long stride_cand, const int* gt, int* rank, int Nq, int Nc, void* stream);
+int valor_dual_softmax(const float* S, float* out, long long stride_norm, long long stride_other, const float* temp, int Nnorm, int Nother, void* stream);
+
 /* ---- optimizer step: optim/adamw.py:50-101 + clip_grad_norm_ (train_utils.py:359) ------------- */
 int valor_grad_sumsq(const float* g, long long n, float* out, void* stream);
 int valor_clip_coef(const float* sumsq, float max_norm, float* norm_out, void* stream);

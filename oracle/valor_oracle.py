@@ -451,6 +451,50 @@ def forward_pt(batch, sd, geom, txt_input, txt_labels, task="pt_contra%tva%tv%ta
 
 
 # --------------------------------------------------------------------------------------
+# retrieval evaluation  (test.py:249-411,680-775)
+# --------------------------------------------------------------------------------------
+
+
+def compute_metric_ret(score_matrix, ids, ids_txt, temp=None, dual_softmax=False, evaluate_ret_text=False):
+    """compute_metric_ret, test.py:714-775 (+ compute_dualsoftmax_forward/backward :680-713): full sort per query on the
+    score matrix [len(ids_txt), len(ids)], then the position of the ground-truth candidate in the sorted index list."""
+    fwd = score_matrix
+    if dual_softmax:
+        fwd = score_matrix * F.softmax(score_matrix / temp, dim=0) * len(score_matrix)
+    idx1 = fwd.sort(dim=-1, descending=True)[1].tolist()
+    rank = torch.tensor([idx1[i].index(ids.index(ids_txt[i])) for i in range(len(ids_txt))]).float()
+
+    def summary(r, n, prefix):
+        r1, r5, r10 = [(r < k).sum().item() / n for k in (1, 5, 10)]
+        return {f"{prefix}_recall": f"{round(r1 * 100, 1)}/{round(r5 * 100, 1)}/{round(r10 * 100, 1)}",
+                f"{prefix}_ravg": round((r1 + r5 + r10) / 3 * 100, 1),
+                f"{prefix}_medianR": torch.median(r).item() + 1, f"{prefix}_meanR": torch.mean(r).item() + 1}
+
+    log = summary(rank, len(ids_txt), "forward")
+    if evaluate_ret_text:
+        bwd = score_matrix
+        if dual_softmax:
+            bwd = score_matrix * F.softmax(score_matrix / temp, dim=1) * len(score_matrix[0])
+        idx2 = bwd.sort(dim=0, descending=True)[1].permute(1, 0).tolist()
+        r2 = []
+        for i in range(len(ids)):
+            gts = [j for j, t in enumerate(ids_txt) if t == ids[i]]
+            r2.append(min(idx2[i].index(j) for j in gts))
+        log.update(summary(torch.tensor(r2).float(), len(ids), "backward"))
+    return log
+
+
+def retrieval_scores(feat_t, feat_v, feat_a, tokens, sd, group):
+    """the per-group score matrix of validate_ret (test.py:303-345) for contra_type='fine' with learned fine weights"""
+    fb = {"tva": torch.cat((feat_v, feat_a), dim=1) if feat_a is not None and feat_v is not None else None, "tv": feat_v, "ta": feat_a}[group]
+    wb = {"tva": lambda: torch.cat((fine_weight(feat_v, sd, "video"), fine_weight(feat_a, sd, "audio")), dim=1),
+          "tv": lambda: fine_weight(feat_v, sd, "video"), "ta": lambda: fine_weight(feat_a, sd, "audio")}[group]()
+    maskA = (tokens != 0).long()
+    maskB = torch.ones(*fb.shape[:2], dtype=torch.long)
+    return compute_fine_matrix(feat_t, fb, maskA, maskB, fine_weight(feat_t, sd, "text"), wb)
+
+
+# --------------------------------------------------------------------------------------
 # optimizer step  (optim/adamw.py, optim/sched.py, optim/misc.py, train_utils.py:344-363)
 # --------------------------------------------------------------------------------------
 

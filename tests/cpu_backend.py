@@ -334,6 +334,16 @@ def row_scale(x, scale, rows_per_group, residual=None):
     return y.to(x.dtype)
 
 
+def retrieval_rank(S, gt, by_column=False):
+    M = S.t() if by_column else S
+    ref = M.gather(1, gt.long()[:, None])
+    return (M > ref).sum(1).int()
+
+
+def dual_softmax(S, temp, dim):
+    return S * torch.softmax(S / temp, dim=dim) * S.shape[dim]
+
+
 def split_bf16x3(x, side):
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16)

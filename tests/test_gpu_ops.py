@@ -464,3 +464,61 @@ def test_droppath_scale_and_row_scale():
     want = x * s8.cpu().repeat_interleave(49)[:, None] + r
     close(got, want, torch.bfloat16, "row_scale")
     close(k.row_scale(dev(x, torch.bfloat16), s8, 49), x * s8.cpu().repeat_interleave(49)[:, None], torch.bfloat16, "row_scale bwd")
+
+
+# ------------------------------------------------------------------------------------------
+# retrieval evaluation (test.py:680-775)
+# ------------------------------------------------------------------------------------------
+def test_retrieval_rank_and_dual_softmax():
+    k = K()
+    g = torch.Generator().manual_seed(3)
+    S = torch.randn(700, 333, generator=g)
+    gt = torch.randint(0, 333, (700,), generator=g).int()
+    close_i = lambda a, b: torch.equal(a.cpu().long(), b.long())
+    assert close_i(k.retrieval_rank(S.cuda(), gt.cuda()), (S > S.gather(1, gt.long()[:, None])).sum(1))
+    gc = torch.randint(0, 700, (333,), generator=g).int()
+    assert close_i(k.retrieval_rank(S.cuda(), gc.cuda(), by_column=True), (S.t() > S.t().gather(1, gc.long()[:, None])).sum(1))
+    temp = torch.tensor([0.07])
+    for dim in (0, 1):
+        want = S * torch.softmax(S / temp, dim=dim) * S.shape[dim]
+        torch.testing.assert_close(k.dual_softmax(S.cuda(), temp.cuda(), dim).cpu(), want, rtol=2e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_retrieval_scoring_at_the_msrvtt_size(dtype):
+    """BASELINE configs[4]: 1 000 clips x 1 000 captions, text 32 tokens, 8 frame + 2 audio slots, d = 512.  The score
+    matrix of the one-GEMM + max/max reduction path against the reference's einsum formulation (pretrain.py:200-209) on
+    a 64 x 1000 slice in fp64, and the device ranks against sort + index."""
+    import types
+    from valor_b200 import retrieval as R
+    from valor_b200 import functional as Fn
+    k = K()
+    g = torch.Generator().manual_seed(5)
+    Nt = Nv = 1000
+    T, nV, nA, D = 32, 8, 2, 512
+    ft = torch.nn.functional.normalize(torch.randn(Nt, T, D, generator=g), dim=-1)
+    fv = torch.nn.functional.normalize(torch.randn(Nv, nV, D, generator=g), dim=-1)
+    fa = torch.nn.functional.normalize(torch.randn(Nv, nA, D, generator=g), dim=-1)
+    lens = torch.randint(8, 31, (Nt,), generator=g)
+    tokens = (torch.arange(T)[None, :] < lens[:, None]).long() * 1000
+    w_t, w_v, w_a = torch.randn(Nt, T, generator=g), torch.randn(Nv, nV, generator=g), torch.randn(Nv, nA, generator=g)
+    maskA = (tokens != 0).to(torch.uint8)
+    split = dtype == torch.bfloat16
+    sc = Fn.FineSimFn.apply(ft.reshape(-1, D).cuda(), torch.cat((fv, fa), 1).reshape(-1, D).cuda(), w_t.cuda(), w_v.cuda(), w_a.cuda(),
+                            maskA.cuda(), (Nt, Nv, T, nV, nA), ["tva"], split)[0]
+    torch.cuda.synchronize()
+    # reference formulation on a slice (pretrain.py:193-209), float64
+    A, B = ft[:64].double(), torch.cat((fv, fa), 1).double()
+    wa = w_t[:64].double().masked_fill(maskA[:64] == 0, float("-inf")).softmax(-1)
+    wb = torch.cat((w_v, w_a), 1).double().softmax(-1)
+    L = torch.einsum("atd,bvd->abtv", A, B) * maskA[:64].double()[:, None, :, None]
+    want = 0.5 * ((L.max(-1)[0] * wa[:, None, :]).sum(-1) + (L.max(-2)[0] * wb[None, :, :]).sum(-1))
+    torch.testing.assert_close(sc[:64].cpu().double(), want, rtol=2e-4, atol=2e-5)
+    ids = [f"v{i}" for i in range(Nv)]
+    perm = torch.randperm(Nt, generator=g).tolist()
+    ids_txt = [f"v{p}" for p in perm]
+    model = types.SimpleNamespace(contra_temp=types.SimpleNamespace(data=torch.tensor(0.07).cuda()))
+    log = R.compute_metric_ret(model, sc, ids, ids_txt, evaluate_ret_text=True)
+    order = sc.cpu().sort(dim=-1, descending=True)[1]
+    rank = torch.tensor([(order[i] == perm[i]).nonzero().item() for i in range(Nt)]).float()
+    assert log["forward_meanR"] == rank.mean().item() + 1 and log["forward_medianR"] == rank.median().item() + 1

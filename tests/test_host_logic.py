@@ -190,3 +190,42 @@ def test_stochastic_mode_gradients_match_finite_differences(cpu_kernels):
             p.data.view(-1)[idx] += eps
         fd = (lp - lm) / (2 * eps)
         assert abs(fd - g) <= 3e-2 * max(abs(g), abs(fd)) + 1e-4, (name, fd, g)
+
+
+def test_retrieval_path_matches_the_oracle(cpu_kernels):
+    """forward_ret evaluation dict + validate_ret scoring + on-device recall (test.py:249-411,714-775) against the
+    oracle's compute_fine_matrix + sort/index ranking on the same features; several captions per clip."""
+    from oracle import valor_oracle as vo
+    from valor_b200 import retrieval as R
+    golden = json.load(open(os.path.join(HERE, "golden", "golden_tiny.json")))
+    model, batch = build(golden["config"])
+    geom = synth.TINY
+    batches = []
+    for i in range(3):     # 3 batches x 2 captions; clips repeat so that some clips own two captions
+        b = synth.make_batch(2, 2, 1, 16, geom, seed=200 + i)
+        b["ids"] = [f"clip{(2 * i) % 4}", f"clip{(2 * i + 1) % 4}"]
+        batches.append(b)
+    ev = [model(b, "ret%tva%tv", compute_loss=False) for b in batches]
+    assert set(ev[0]) == {"feat_t", "feat_v", "feat_a", "txt_tokens"}
+    # candidates = one entry per distinct clip (first occurrence), captions = all 6
+    ids_txt = [i for b in batches for i in b["ids"]]
+    first = {}
+    for n, cid in enumerate(ids_txt):
+        first.setdefault(cid, n)
+    ids = list(first)
+    feat_t = torch.cat([e["feat_t"] for e in ev]); toks = torch.cat([e["txt_tokens"] for e in ev])
+    feat_v = torch.cat([e["feat_v"] for e in ev])[[first[c] for c in ids]]
+    feat_a = torch.cat([e["feat_a"] for e in ev])[[first[c] for c in ids]]
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    for group in ("tva", "tv"):
+        want = vo.retrieval_scores(feat_t.float(), feat_v.float(), feat_a.float(), toks, sd, group)
+        got = R._fine_scores(model, feat_t, feat_v, feat_a, toks, group)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+        for dual in (False, True):
+            ref = vo.compute_metric_ret(want, ids, ids_txt, temp=sd["contra_temp"], dual_softmax=dual, evaluate_ret_text=True)
+            log = R.compute_metric_ret(model, got, ids, ids_txt, dual_softmax=dual, evaluate_ret_text=True)
+            assert log == ref, (group, dual, log, ref)
+    # the loss side of forward_ret: the contrastive loss without the pretraining ratio (pretrain.py:699)
+    l_ret = model(batches[0], "ret%tva%tv", compute_loss=True)["contra_loss"].item()
+    l_pt = model(batches[0], "pt_contra%tva%tv", compute_loss=True)["contra_loss"].item()
+    assert abs(l_ret * 1.5 - l_pt) <= 1e-6 * abs(l_pt)

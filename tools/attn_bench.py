@@ -33,7 +33,7 @@ def window(B, grid_hw, heads, shift, name, D=8, backend=0):
     geom = ((B, D, H, W), (min(D, 8), 7, 7), shift, (8, 7, 7), heads, hd, hd ** -0.5)
     N = min(D, 8) * 49
     o, lse = K.window_attn_fwd(qkv, table, *geom, backend=backend)
-    dt = torch.zeros_like(table)
+    dt = None if "--nodtab" in sys.argv else torch.zeros_like(table)
     ms_f = bench(lambda: K.window_attn_fwd(qkv, table, *geom, backend=backend))
     ms_b = bench(lambda: K.window_attn_bwd(qkv, o, do, lse, table, dt, *geom, backend=backend))
     nprob = B * (D // min(D, 8)) * (H // 7) * (W // 7) * heads

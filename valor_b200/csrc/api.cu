@@ -63,6 +63,8 @@ int split_bf16x3(const float* x, long long xld, void* out, long long R, long lon
 int dropout_apply(int, const void*, long long, const void*, long long, void*, long long, long long, int, float, const long long*, long long, cudaStream_t);
 int droppath_scale(float*, int, float, const long long*, long long, cudaStream_t);
 int row_scale(int, const void*, long long, const float*, long long, const void*, long long, void*, long long, long long, int, cudaStream_t);
+int retrieval_rank(const float*, long long, long long, const int*, int*, int, int, cudaStream_t);
+int dual_softmax(const float*, float*, long long, long long, const float*, int, int, cudaStream_t);
 bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
                        const void* k, const void* v, const void* o);
 int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
@@ -343,6 +345,12 @@ int valor_contrastive_fwd(const float* S, const float* temp, float* row_lse, flo
 }
 int valor_contrastive_bwd(const float* S, const float* temp, const float* row_lse, const float* col_lse, const float* gptr, float gmul, float* dS, float* dtemp, int N, void* stream) {
   return contrastive_bwd(S, temp, row_lse, col_lse, gptr, gmul, dS, dtemp, N, ST);
+}
+int valor_retrieval_rank(const float* S, long long stride_query, long long stride_cand, const int* gt, int* rank, int Nq, int Nc, void* stream) {
+  return retrieval_rank(S, stride_query, stride_cand, gt, rank, Nq, Nc, ST);
+}
+int valor_dual_softmax(const float* S, float* out, long long stride_norm, long long stride_other, const float* temp, int Nnorm, int Nother, void* stream) {
+  return dual_softmax(S, out, stride_norm, stride_other, temp, Nnorm, Nother, ST);
 }
 int valor_grad_sumsq(const float* g, long long n, float* out, void* stream) { return grad_sumsq(g, n, out, ST); }
 int valor_clip_coef(const float* sumsq, float max_norm, float* norm_out, void* stream) { return clip_coef(sumsq, max_norm, norm_out, ST); }

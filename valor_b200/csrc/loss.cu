@@ -286,4 +286,57 @@ int contrastive_bwd(const float* S, const float* temp, const float* row_lse, con
   return check_launch("contrastive_bwd_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------
+// retrieval ranks (test.py:714-775 compute_metric_ret): the reference sorts every row of the score matrix on the
+// device, copies the index matrix to the host and looks the ground truth up with list.index (O(N^2) Python).  The
+// rank of the ground truth is simply the number of candidates that score higher: one warp per query,
+//   rank[i] = #{ j : S[i*sr + j*sc] > S[i*sr + gt[i]*sc] }       (sr/sc strides: rows or columns of the matrix)
+// dual softmax (test.py:685-713, off in every shipped config) rescales the scores first:
+//   S'[i,j] = S[i,j] * softmax(S[:,j] / temp)[i] * n      (forward direction: softmax down the columns)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+retrieval_rank_kernel(const float* __restrict__ S, long long sr, long long sc, const int* __restrict__ gt, int* __restrict__ rank,
+                      int Nq, int Nc) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= Nq) return;
+  const float* row = S + (long long)i * sr;
+  const float ref = row[(long long)gt[i] * sc];
+  int cnt = 0;
+  for (int j = lane; j < Nc; j += 32) cnt += row[(long long)j * sc] > ref ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) rank[i] = cnt;
+}
+// out[i,j] = S[i,j] * softmax_over_i(S[:,j] / temp)[i] * Nr   (one block per column j; dim = 1: over j per row i via strides)
+__global__ void __launch_bounds__(256)
+dual_softmax_kernel(const float* __restrict__ S, float* __restrict__ out, long long sr, long long sc, const float* __restrict__ temp,
+                    int Nr, int Nc) {
+  __shared__ float sh[32];
+  const int j = blockIdx.x;
+  const float it = 1.0f / temp[0];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < Nr; i += blockDim.x) m = fmaxf(m, S[(long long)i * sr + (long long)j * sc] * it);
+  m = block_max(m, sh);
+  float z = 0.f;
+  for (int i = threadIdx.x; i < Nr; i += blockDim.x) z += __expf(S[(long long)i * sr + (long long)j * sc] * it - m);
+  z = block_sum(z, sh);
+  const float sc_out = (float)Nr / z;
+  for (int i = threadIdx.x; i < Nr; i += blockDim.x) {
+    const float v = S[(long long)i * sr + (long long)j * sc];
+    out[(long long)i * sr + (long long)j * sc] = v * __expf(v * it - m) * sc_out;
+  }
+}
+int retrieval_rank(const float* S, long long sr, long long sc, const int* gt, int* rank, int Nq, int Nc, cudaStream_t st) {
+  if (Nq == 0) return 0;
+  retrieval_rank_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(S, sr, sc, gt, rank, Nq, Nc);
+  return check_launch("retrieval_rank_kernel");
+}
+int dual_softmax(const float* S, float* out, long long sr, long long sc, const float* temp, int Nr, int Nc, cudaStream_t st) {
+  if (Nr == 0 || Nc == 0) return 0;
+  dual_softmax_kernel<<<Nc, 256, 0, st>>>(S, out, sr, sc, temp, Nr, Nc);
+  return check_launch("dual_softmax_kernel");
+}
+
 }  // namespace valor

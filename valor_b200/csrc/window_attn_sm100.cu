@@ -116,7 +116,9 @@ struct FwdSmem {
   unsigned char *Qs, *Ks, *Vs, *Pp;
   int* qrow; uint32_t *qcode, *kcode, *qreg;
   float* tab2;          // bias slice * log2e
-  float* xch;           // [2 tile parities][2 stats: max, sum][2 halves][128 rows]
+  float* xch;           // [3][4 column slices][128 rows]: row sums of the even / odd tile, exact-maximum exchange
+  float* qn;            // [512] |q_i| * scale * log2e
+  float* red;           // [0] max|k|, [1] max bias, [2] bias range; [4..] per-warp partials
   uint64_t* bars;       // s_full, s_free, o_full[2], p_full[8]
   uint32_t* tmem_slot;
 };
@@ -128,7 +130,7 @@ static inline size_t fwd_smem_bytes(int nqt, int NPK, int np, int n_used) {
   b += (size_t)np * 16384;                           // P panels
   b += (size_t)4 * 512 * 4;                          // qrow qcode kcode qreg (512 entries each)
   b += ((size_t)n_used * 4 + 15) / 16 * 16;
-  b += 2 * 2 * 2 * 128 * 4;
+  b += 3 * 4 * 128 * 4 + 512 * 4 + 128 * 4;
   b += 16 * 8 + 16;
   return b;
 }
@@ -147,7 +149,9 @@ __device__ __forceinline__ FwdSmem fwd_carve(unsigned char* raw, const FwdParams
   S.qreg = S.kcode + 512;
   S.tab2 = (float*)(S.qreg + 512);
   S.xch = (float*)((unsigned char*)S.tab2 + ((size_t)P.n_used * 4 + 15) / 16 * 16);
-  S.bars = (uint64_t*)(S.xch + 2 * 2 * 2 * 128);
+  S.qn = S.xch + 3 * 4 * 128;
+  S.red = S.qn + 512;
+  S.bars = (uint64_t*)(S.red + 128);
   S.tmem_slot = (uint32_t*)(S.bars + 16);
   return S;
 }
@@ -212,146 +216,167 @@ __device__ __forceinline__ void gather_rows(unsigned char* dst, const bf16* src,
 
 constexpr int TMEM_S = 0;        // S columns [0, NPK)
 constexpr int TMEM_O = 448;      // O accumulators: 448..479, 480..511
+constexpr int FEW = 16;          // forward element warps: tensor-memory lane quarter x 16-key column slice of every panel
+constexpr int FET = FEW * 32;
+
+// One 64-key panel slice (16 columns) of one query row: logits -> probabilities against the row reference `ref`
+// (log2 units), row-sum, bf16 pack.  TAIL: only the first nv columns are real keys.
+template <bool MASKED, bool TAIL>
+__device__ __forceinline__ void fwd_cols16(const uint32_t* sv, uint32_t kc_s, uint32_t kr_s, int kg, int nv, uint32_t qaddr, uint32_t qrg,
+                                           float scale2, float ref, float& l_row, uint32_t* pw) {
+  const float kMask2 = -100.0f * kLog2e;          // videoswin.py:284
+  uint32_t kc[16], kr[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 t = lds_v4(kc_s + (kg + g * 4) * 4);
+    kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
+    if (MASKED) {
+      const uint4 u = lds_v4(kr_s + (kg + g * 4) * 4);
+      kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
+    }
+  }
+  float pf[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = fmaf(__uint_as_float(sv[j]), scale2, lds_f32(qaddr - kc[j]));
+    if (MASKED && qrg != kr[j]) x += kMask2;
+    float pr = ex2f(x - ref);
+    if (TAIL && j >= nv) pr = 0.f;
+    pf[j] = pr;
+    l_row += pr;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]);
+}
 
 template <bool MASKED>
-__device__ __forceinline__ void fwd_element_warps(const FwdParams& P, const FwdSmem& S, int p, int h, uint32_t tmem) {
+__device__ __forceinline__ void fwd_element_warps(const FwdParams& P, const FwdSmem& S, int p, int h, uint32_t tmem, bool need_exact) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = warp - 4;
-  const int qtr = e & 3, half = e >> 2;           // tensor-memory lane quarter (hardware: warp % 4), panel parity
+  const int qtr = e & 3, grp = e >> 2;            // tensor-memory lane quarter (hardware: warp % 4), column slice of each panel
   const int N = P.win.N;
   const uint32_t lane_t = tmem + ((uint32_t)(qtr * 32) << 16);
   uint64_t* s_full = S.bars; uint64_t* s_free = S.bars + 1; uint64_t* o_full = S.bars + 2; uint64_t* p_full = S.bars + 4;
   const uint32_t tab_s = s_u32(S.tab2), kc_s = s_u32(S.kcode), kr_s = s_u32(S.qreg);
-  const int rloc = qtr * 32 + lane;               // row inside the 128-query tile
-  float m_prev = 0.f, l_prev = 0.f;
-  const float kMask2 = -100.0f * kLog2e;          // videoswin.py:284
+  const int rloc = qtr * 32 + lane;
+  const int sw = rloc & 7;
+  const float kMask2 = -100.0f * kLog2e;
+  float ref_prev = 0.f;
   for (int qt = 0; qt <= P.nqt; ++qt) {
-    float m_row = -INFINITY, l_row = 0.f;
-    const int q = qt * 128 + rloc;
-    const bool warp_live = qt < P.nqt && (qt * 128 + qtr * 32) < N;
+    const int q0 = qt * 128 + qtr * 32;
+    const int q = q0 + lane;
+    const bool warp_live = qt < P.nqt && q0 < N;
+    float ref = 0.f, l_row = 0.f;
     if (qt < P.nqt) {
       bar_wait(s_full, qt & 1);
       tc_fence_after();
-      if (warp_live) {
-        // ---------------- pass A: logits (log2 units) + row maximum, written back to tensor memory
-        const uint32_t qaddr = tab_s + S.qcode[min(q, 511)];
-        const uint32_t qrg = S.qreg[min(q, 511)];
-        for (int pn = half; pn < P.np; pn += 2) {
-#pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub) {
-            const int c0 = pn * 64 + sub * 32;
-            if (c0 >= P.NPK) break;
-            uint32_t v[32];
-            VALOR_TMEM_LD32(lane_t + TMEM_S + c0, v);
-            uint32_t kc[32], kr[32];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint4 t = lds_v4(kc_s + (c0 + g * 4) * 4);
-              kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
-              if (MASKED) {
-                const uint4 u = lds_v4(kr_s + (c0 + g * 4) * 4);
-                kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
-              }
-            }
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = fmaf(__uint_as_float(v[j]), P.scale2, lds_f32(qaddr - kc[j]));
-              if (MASKED && qrg != kr[j]) x += kMask2;
-              if (c0 + j >= N) x = -INFINITY;           // padding key (warp-uniform)
-              m_row = fmaxf(m_row, x);
-              v[j] = __float_as_uint(x);
-            }
-            VALOR_TMEM_ST32(lane_t + TMEM_S + c0, v);
-          }
-        }
-        tmem_wait_st();
-        S.xch[(((qt & 1) * 2 + 0) * 2 + half) * 128 + rloc] = m_row;
-      }
-      named_bar(1 + qtr, 64);                             // the two warps of this lane quarter exchange their maxima
-      if (warp_live) m_row = fmaxf(m_row, S.xch[(((qt & 1) * 2 + 0) * 2 + (half ^ 1)) * 128 + rloc]);
     }
-    // ---------------- epilogue of the previous tile (its P.V is complete: the panels are free again)
+    // ---------------- epilogue of the previous tile: its P.V has retired (it precedes this tile's S on the tensor pipe),
+    //                  so the panels are free again; 8 output channels per warp
     if (qt > 0) {
       const int pt = qt - 1;
-      if (qt == P.nqt) named_bar(1 + qtr, 64);            // (earlier tiles: the maximum exchange above already ordered the row sums)
+      named_bar(1 + qtr, 128);                          // the quarter's four column-slice warps have published their row sums
       bar_wait(&o_full[pt & 1], (pt >> 1) & 1);
       tc_fence_after();
       const int qp = pt * 128 + rloc;
       if ((pt * 128 + qtr * 32) < N) {
-        uint32_t o[16];
-        VALOR_TMEM_LD16(lane_t + TMEM_O + (pt & 1) * 32 + half * 16, o);
-        const float l_tot = l_prev + S.xch[(((pt & 1) * 2 + 1) * 2 + (half ^ 1)) * 128 + rloc];
+        uint32_t o[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+                     : "r"(lane_t + TMEM_O + (pt & 1) * 32 + grp * 8));
+        const float* xs = S.xch + (pt & 1) * 4 * 128 + rloc;
+        const float l_tot = xs[0] + xs[128] + xs[256] + xs[384];
         tmem_wait_ld();
         if (qp < N) {
           const float inv = 1.0f / l_tot;
-          bf16* dst = P.O + (size_t)S.qrow[qp] * P.ldo + h * HD + half * 16;
-          uint4 w0, w1;
+          bf16* dst = P.O + (size_t)S.qrow[qp] * P.ldo + h * HD + grp * 8;
+          uint4 w0;
           w0.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
           w0.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
           w0.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
           w0.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-          w1.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-          w1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-          w1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-          w1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
           *(uint4*)dst = w0;
-          *(uint4*)(dst + 8) = w1;
-          if (half == 0) P.lse[((size_t)p * P.heads + h) * N + qp] = (m_prev + log2f(l_tot)) * kLn2;
+          if (grp == 0) P.lse[((size_t)p * P.heads + h) * N + qp] = (ref_prev + log2f(l_tot)) * kLn2;
         }
       }
       tc_fence_before();
     }
     if (qt == P.nqt) break;
-    // ---------------- pass B: probabilities, row sum, bf16 panels
-    for (int pn = half; pn < P.np; pn += 2) {
+    const uint32_t qaddr = tab_s + S.qcode[min(q, 511)];
+    const uint32_t qrg = S.qreg[min(q, 511)];
+    // ---------------- row reference: softmax is shift-invariant, so any value within ~2^+-100 of the row maximum works in
+    // fp32 / bf16.  Cheap bound: max_j (q.k_j * scale + bias) <= |q| max_j|k_j| scale + max(bias); the prologue verified
+    // that the bound is within 90 (log2 units) of every row's maximum, otherwise (need_exact) the exact maximum is taken.
+    ref = S.qn[min(q, 511)] * S.red[0] + S.red[1];
+    if (need_exact) {
+      float m = -INFINITY;
       if (warp_live) {
-        const uint32_t prow = s_u32(S.Pp) + pn * 16384 + rloc * 128;
-#pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
-          const int c0 = pn * 64 + sub * 32;
-          if (c0 >= P.NPK) break;
-          uint32_t v[32];
-          VALOR_TMEM_LD32(lane_t + TMEM_S + c0, v);
+        for (int pn = 0; pn < P.np; ++pn) {
+          const int c0 = pn * 64 + grp * 16;
+          const int nv = min(16, N - c0);
+          if (nv <= 0) break;
+          uint32_t sv[16];
+          VALOR_TMEM_LD16(lane_t + TMEM_S + c0, sv);
           tmem_wait_ld();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float pv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              pv[j] = ex2f(__uint_as_float(v[g * 8 + j]) - m_row);
-              l_row += pv[j];
-            }
-            const int ch = sub * 4 + g;
-            const uint32_t a = prow + (uint32_t)((ch ^ (rloc & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pack_bf16(pv[0], pv[1])), "r"(pack_bf16(pv[2], pv[3])),
-                         "r"(pack_bf16(pv[4], pv[5])), "r"(pack_bf16(pv[6], pv[7])) : "memory");
+          for (int j = 0; j < nv; ++j) {
+            float x = fmaf(__uint_as_float(sv[j]), P.scale2, lds_f32(qaddr - S.kcode[c0 + j]));
+            if (MASKED && qrg != S.qreg[c0 + j]) x += kMask2;
+            m = fmaxf(m, x);
           }
         }
+        S.xch[2 * 4 * 128 + grp * 128 + rloc] = m;
+      }
+      named_bar(1 + qtr, 128);
+      if (warp_live) {
+        const float* xm = S.xch + 2 * 4 * 128 + rloc;
+        ref = fmaxf(fmaxf(xm[0], xm[128]), fmaxf(xm[256], xm[384]));
+      }
+      named_bar(1 + qtr, 128);
+    }
+    // ---------------- single pass: probabilities, row sum, bf16 panels
+    for (int pn = 0; pn < P.np; ++pn) {
+      const int c0 = pn * 64 + grp * 16;
+      const int nv = N - c0;
+      if (c0 < P.NPK) {
+        uint32_t pw[8];
+        if (warp_live && nv > 0) {
+          uint32_t sv[16];
+          VALOR_TMEM_LD16(lane_t + TMEM_S + c0, sv);
+          tmem_wait_ld();
+          if (nv >= 16) fwd_cols16<MASKED, false>(sv, kc_s, kr_s, c0, 16, qaddr, qrg, P.scale2, ref, l_row, pw);
+          else fwd_cols16<MASKED, true>(sv, kc_s, kr_s, c0, nv, qaddr, qrg, P.scale2, ref, l_row, pw);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pw[j] = 0u;
+        }
+        const uint32_t prow = s_u32(S.Pp) + pn * 16384 + rloc * 128;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (uint32_t)(((grp * 2) ^ sw) << 4)), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (uint32_t)(((grp * 2 + 1) ^ sw) << 4)), "r"(pw[4]), "r"(pw[5]), "r"(pw[6]), "r"(pw[7]) : "memory");
       }
       proxy_fence();                                      // generic-proxy panel writes -> visible to the MMA unit
       __syncwarp();
       if (lane == 0) bar_arrive(&p_full[pn]);
     }
+    if (warp_live) S.xch[(qt & 1) * 4 * 128 + grp * 128 + rloc] = l_row;   // before the arrive below: ordered for the partners
     tc_fence_before();
     __syncwarp();
     if (lane == 0) bar_arrive(s_free);
-    if (warp_live) S.xch[(((qt & 1) * 2 + 1) * 2 + half) * 128 + rloc] = l_row;
-    m_prev = m_row; l_prev = l_row;
+    ref_prev = ref;
   }
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(128 + FET, 1)
 window_fwd_sm100_kernel(FwdParams P) {
   extern __shared__ unsigned char smem_raw[];
   const FwdSmem S = fwd_carve(smem_raw, P);
   const int p = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.heads * HD, col0 = h * HD;
+  const int N = P.win.N;
   uint64_t* s_full = S.bars; uint64_t* s_free = S.bars + 1; uint64_t* o_full = S.bars + 2; uint64_t* p_full = S.bars + 4;
   if (threadIdx.x == 0) {
-    bar_init(s_full, 1); bar_init(s_free, 8); bar_init(&o_full[0], 1); bar_init(&o_full[1], 1);
-    for (int i = 0; i < 8; ++i) bar_init(&p_full[i], 4);
+    bar_init(s_full, 1); bar_init(s_free, FEW); bar_init(&o_full[0], 1); bar_init(&o_full[1], 1);
+    for (int i = 0; i < 8; ++i) bar_init(&p_full[i], FEW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -364,10 +389,46 @@ window_fwd_sm100_kernel(FwdParams P) {
   gather_rows(S.Ks, P.qkv + C, P.ld, col0, S.qrow, P.NPK);
   gather_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.qrow, P.NPK);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  // bias range of this head's table slice (log2 units)
+  float bmax = -INFINITY, bmin = INFINITY;
+  for (int r = threadIdx.x; r < P.n_used; r += blockDim.x) { const float v = S.tab2[r]; bmax = fmaxf(bmax, v); bmin = fminf(bmin, v); }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // row norms: |q_i| per query row, max_j |k_j|
+  float knmax = 0.f;
+  for (int r = threadIdx.x; r < 512 + P.NPK; r += blockDim.x) {
+    const bool isq = r < 512;
+    const int row = isq ? r : r - 512;
+    float ss = 0.f;
+    if (!isq || row < P.nqt * 128) {
+      const unsigned char* base = isq ? S.Qs : S.Ks;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint4 a = *(const uint4*)(base + tile64(row, ch));
+        const __nv_bfloat162* pa = (const __nv_bfloat162*)&a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(pa[j]); ss += f.x * f.x + f.y * f.y; }
+      }
+    }
+    const float nrm = sqrtf(ss);
+    if (isq) S.qn[row] = nrm * P.scale2;      // |q_i| * scale * log2e
+    else knmax = fmaxf(knmax, nrm);
+  }
+  knmax = warp_max(knmax); bmax = warp_max(bmax); bmin = -warp_max(-bmin);
+  if (lane == 0) { S.red[4 + warp] = knmax; S.red[4 + 32 + warp] = bmax; S.red[4 + 64 + warp] = bmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = -INFINITY, c = INFINITY;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a = fmaxf(a, S.red[4 + w]); b = fmaxf(b, S.red[4 + 32 + w]); c = fminf(c, S.red[4 + 64 + w]); }
+    S.red[0] = a; S.red[1] = b; S.red[2] = b - c;
+  }
+  __syncthreads();
+  // the bound max_j logit <= |q_i| kmax scale + bmax overshoots the true row maximum by at most 2 |q_i| kmax scale + (bmax - bmin)
+  int loose = 0;
+  for (int r = threadIdx.x; r < N; r += blockDim.x) loose |= (2.f * S.qn[r] * S.red[0] + S.red[2] > 90.f) ? 1 : 0;
   proxy_fence();
   tc_fence_before();
-  __syncthreads();
+  const bool need_exact = __syncthreads_or(loose) != 0;
   tc_fence_after();
   const uint32_t tmem = *S.tmem_slot;
 
@@ -402,8 +463,8 @@ window_fwd_sm100_kernel(FwdParams P) {
       }
     }
   } else if (warp >= 4) {
-    if (masked) fwd_element_warps<true>(P, S, p, h, tmem);
-    else fwd_element_warps<false>(P, S, p, h, tmem);
+    if (masked) fwd_element_warps<true>(P, S, p, h, tmem, need_exact);
+    else fwd_element_warps<false>(P, S, p, h, tmem, need_exact);
   }
   tc_fence_before();
   __syncthreads();
@@ -412,7 +473,6 @@ window_fwd_sm100_kernel(FwdParams P) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
   }
 }
-
 
 // ==========================================================================================
 // backward
@@ -886,7 +946,7 @@ int window_sm100_fwd(const WindowIndex& ix, const void* qkv, long long ld, void*
   const size_t smem = fwd_smem_bytes(P.nqt, P.NPK, P.np, P.n_used);
   static size_t attr = 0;
   if (smem > attr) { VALOR_CUDA(cudaFuncSetAttribute(window_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  window_fwd_sm100_kernel<<<dim3(Pn, H), 384, smem, st>>>(P);
+  window_fwd_sm100_kernel<<<dim3(Pn, H), 128 + FET, smem, st>>>(P);
   return check_launch("window_fwd_sm100_kernel");
 }
 

@@ -397,6 +397,28 @@ def contrastive_bwd(S, temp, row_lse, col_lse, g, dtemp, gmul=1.0):
     return dS
 
 
+def retrieval_rank(S, gt, by_column=False):
+    """rank[i] = #{candidates scoring above query i's ground truth}.  S [Nt, Nv] fp32 row-major; by_column: queries are
+    the columns (video -> text direction)."""
+    Nt, Nv = S.shape
+    Nq, Nc = (Nv, Nt) if by_column else (Nt, Nv)
+    sq, sc = (1, S.stride(0)) if by_column else (S.stride(0), 1)
+    rank = torch.empty(Nq, device=S.device, dtype=torch.int32)
+    _call("valor_retrieval_rank", P(S), sq, sc, P(gt), P(rank), Nq, Nc, ST())
+    return rank
+
+
+def dual_softmax(S, temp, dim):
+    """S * softmax(S / temp, dim) * S.shape[dim]  (test.py:685-713)"""
+    Nt, Nv = S.shape
+    out = torch.empty_like(S)
+    if dim == 0:
+        _call("valor_dual_softmax", P(S), P(out), S.stride(0), 1, P(temp), Nt, Nv, ST())
+    else:
+        _call("valor_dual_softmax", P(S), P(out), 1, S.stride(0), P(temp), Nv, Nt, ST())
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # optimizer
 # ------------------------------------------------------------------------------------------

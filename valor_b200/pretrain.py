@@ -48,16 +48,30 @@ class VALOR(VALORModel):
 
     # ------------------------------------------------------------------------------------
     def forward(self, batch, task, compute_loss=True):
-        if task.startswith("pt"):
-            if self.store is not None and self.training:
-                cache = self.__dict__.setdefault("_unused_cache", {})
-                if task not in cache:
-                    cache[task] = self.unused_parameter_names(task)
-                self.store.set_unused(cache[task])
-            if self.store is not None and self.training and self.rng.active:
+        if not (task.startswith("pt") or task.startswith("ret")):
+            raise NotImplementedError("cap / qa decoding heads are outside the scope table (SURVEY.md §8f N3)")
+        eff = task if task.startswith("pt") else "pt_contra%" + "%".join(task.split("%")[1:])
+        if self.store is not None and self.training:
+            cache = self.__dict__.setdefault("_unused_cache", {})
+            if eff not in cache:
+                cache[eff] = self.unused_parameter_names(eff)
+            self.store.set_unused(cache[eff])
+            if self.rng.active:
                 self.rng.begin_step()     # new masks every forward (also under CUDA-graph replay: see RngState)
+        if task.startswith("pt"):
             return self.forward_pt(batch, task, compute_loss=compute_loss)
-        raise NotImplementedError("ret/cap/qa heads are the next §8 rows (SURVEY.md §8f N1-N3)")
+        return self.forward_ret(batch, task, compute_loss=compute_loss)
+
+    def forward_ret(self, batch, task, compute_loss=True):
+        """pretrain.py:544-711: the retrieval head = the contrastive branch of forward_pt alone.  compute_loss=False
+        returns {'feat_t','feat_v','feat_a','txt_tokens'} for valor_b200.retrieval.validate_ret; compute_loss=True the
+        fine-grained contrastive loss over the requested groups WITHOUT the pretraining loss ratio (:699)."""
+        groups = task.split("%")[1:]
+        pt_task = "pt_contra%" + "%".join(groups)
+        out = self.forward_pt(batch, pt_task, compute_loss=compute_loss)
+        if compute_loss:
+            return {"contra_loss": out["contra_loss"] / self.contra_loss_ratio}
+        return out
 
     def unused_parameter_names(self, task):
         """Parameters that receive no gradient under `task` (the reference runs DDP with
