@@ -679,7 +679,11 @@ __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdS
       for (int sub = 0; sub < 2; ++sub) {
         const int c0 = grp * 32 + sub * 16;               // column inside the 128-key block
         const int nv = nvk - sub * 16;                    // real keys among these 16 columns
+#if defined(VALOR_EXP) && (VALOR_EXP & 2)
+        if (false) {
+#else
         if (live && nv > 0) {
+#endif
           uint32_t sv[16], dv[16];
           VALOR_TMEM_LD16(lane_t + TB_S + c0, sv);
           VALOR_TMEM_LD16(lane_t + TB_DP + c0, dv);
@@ -832,6 +836,9 @@ window_bwd_sm100_kernel(BwdParams P) {
   tc_fence_after();
   const uint32_t tmem = *S.tmem_slot;
   const int nb = P.nkt * P.nqt;
+#if defined(VALOR_EXP) && (VALOR_EXP & 4)
+  if (true) { tc_fence_before(); __syncthreads(); if (warp == 1) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)); } return; }
+#endif
 
   if (warp == 0) {
     if (lane == 0) {
@@ -864,6 +871,9 @@ window_bwd_sm100_kernel(BwdParams P) {
         const int kq = (min(128, N - qt * 128) + 15) / 16;       // 16-query k-steps that hold real rows
         const int kk = (min(128, N - kt * 128) + 15) / 16;       // 16-key k-steps that hold real keys
         const uint32_t tkv = tmem + TB_DKV + (kt & 1) * 64;
+#if defined(VALOR_EXP) && (VALOR_EXP & 1)
+        if (false)
+#endif
         for (int ks = 0; ks < kq; ++ks) {
           const uint64_t bq = smem_desc(Qs + (qt * 128 + ks * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4);
           const uint64_t bo = smem_desc(dOs + (qt * 128 + ks * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4);
@@ -871,6 +881,9 @@ window_bwd_sm100_kernel(BwdParams P) {
           tc_mma(tkv, smem_desc(dSb + ks * 2048, 16384, 1024, 2), bq, id_kv, acc);        // dK += dS^T . Q
           tc_mma(tkv + 32, smem_desc(Pb + ks * 2048, 16384, 1024, 2), bo, id_kv, acc);    // dV += P^T . dO
         }
+#if defined(VALOR_EXP) && (VALOR_EXP & 1)
+        if (false)
+#endif
         for (int ks = 0; ks < kk; ++ks)                                                   // dQ += dS . K
           tc_mma(tmem + TB_DQ + qt * 32, smem_desc(dSb + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024, 2),
                  smem_desc(Ks + ks * 16 * ROWB, VALOR_SW64_MN_LBO, 512, 4), id_q, (kt | ks) ? 1u : 0u);

@@ -94,6 +94,11 @@ class AudioEmbeddings(nn.Module):
         self.hidden_dropout = model_cfg_audio.hidden_dropout   # modeling.py:748,761
         self.register_buffer("_anchor", torch.zeros(1), persistent=False)
 
+    def forward(self, audio_spectrograms):
+        """Reference signature (modeling.py:750-762): [N, mel, frames] -> [N, P+1, H]."""
+        N = audio_spectrograms.shape[0]
+        return self.run(audio_spectrograms, self.cls_token.lp.dtype).view(N, self.token_length_per_frame + 1, -1)
+
     def run(self, spec, dtype):
         """spec [N, mel, frames] -> [N*(P+1), H]   (conv-as-GEMM, cls + position, modeling.py:750-762)."""
         N = spec.shape[0]
