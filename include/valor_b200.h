@@ -89,6 +89,9 @@ int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm,
  * others do not exist for it (excluded from the softmax, not -10000).  This is how the three caption passes of one
  * sample (tva / tv / ta, pretrain.py:455-479: same text rows, video+audio / video / audio media tokens as
  * cross-attention source, bert.py:450) run as ONE problem over the sample's media tokens.
+ * drop_p > 0: attention-probability dropout (bert.py:283,334; transformer.py:128): P.V uses keep * P / (1-p) with
+ * keep(i,j) regenerated in the backward from rng_state = {seed, step offset} (int64[2], device), `site`, (problem, head) and
+ * the (query, key) index; the log-sum-exp stays that of the undropped softmax.  Tensor-core path only.
  * lse [P,H,Nq] fp32 is saved for the backward.
  * Backward: dQ written.  dK/dV either accumulate (+=) into fp32 [rows, H*hd] buffers the caller zero-fills
  * (dK/dV: K/V rows shared by several problems add up — cross-attention), or, when every K/V row belongs to
@@ -98,13 +101,15 @@ int valor_l2norm_bwd(int dtype, const void* dy, const void* x, const float* nrm,
 int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
                   void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid, const unsigned char* causal,
-                  const int* q_key_range, float scale, int backend, void* stream);
+                  const int* q_key_range, float scale, float drop_p, const long long* rng_state, long long site, int backend,
+                  void* stream);
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                   long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta,
                   void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp,
                   void* dV_lp, long long lddkv_lp, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid,
-                  const unsigned char* causal, const int* q_key_range, float scale, int backend, void* stream);
+                  const unsigned char* causal, const int* q_key_range, float scale, float drop_p, const long long* rng_state,
+                  long long site, int backend, void* stream);
 
 /* ---- VideoSwin shifted-window attention: WindowAttention3D.forward (videoswin.py:137-163)
  * together with torch.roll / window_partition / window_reverse / compute_mask

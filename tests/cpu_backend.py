@@ -123,8 +123,22 @@ def _range_mask(add, q_key_range, nk):
     return (add + torch.zeros(r.shape[0], nk)).masked_fill(out, float("-inf"))
 
 
+KEEP_OVERRIDE = None   # tests: {(p, h): keep mask [Nq, nk]} extracted from the CUDA kernels
+
+
+def _attn_keep(drop, p, h, Nq, nk):
+    """keep / (1-p) factor of attention-probability dropout for problem p, head h (None: no dropout)"""
+    if drop is None:
+        return None
+    pd, state, site = drop
+    if KEEP_OVERRIDE is not None:
+        return KEEP_OVERRIDE[(p, h)][:, :nk].float() / (1.0 - pd)
+    g = torch.Generator().manual_seed(int(state[0]) * 1000003 + int(state[1]) * 7919 + int(site) * 131 + p * 17 + h)
+    return (torch.rand(Nq, nk, generator=g) >= pd).float() / (1.0 - pd)
+
+
 def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None, key_valid=None,
-            causal=None, q_key_range=None, backend=0):
+            causal=None, q_key_range=None, backend=0, drop=None):
     o = torch.zeros(q.shape[0], H * hd, dtype=q.dtype)
     lse = torch.zeros(P_, H, Nq)
     for p in range(P_):
@@ -136,12 +150,16 @@ def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv
             vv = v[k0:k0 + nk, h * hd:(h + 1) * hd].float()
             s = qq @ kk.t() * scale + add
             lse[p, h] = torch.logsumexp(s, -1)
-            o[q0:q0 + Nq, h * hd:(h + 1) * hd] = (torch.softmax(s, -1) @ vv).to(q.dtype)
+            pr = torch.softmax(s, -1)
+            keep = _attn_keep(drop, p, h, Nq, nk)
+            if keep is not None:
+                pr = pr * keep
+            o[q0:q0 + Nq, h * hd:(h + 1) * hd] = (pr @ vv).to(q.dtype)
     return o, lse
 
 
 def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
-            key_valid=None, causal=None, dkv_out=None, q_key_range=None, backend=0):
+            key_valid=None, causal=None, dkv_out=None, q_key_range=None, backend=0, drop=None):
     dkv = torch.zeros(k.shape[0], 2 * H * hd)
     for p in range(P_):
         q0, k0, nk = _mha_problem(p, Nq, max_nk, q_row0, kv_row0, kv_len)
@@ -152,10 +170,15 @@ def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=No
             dd, oo = do[q0:q0 + Nq, sl].float(), o[q0:q0 + Nq, sl].float()
             pr = torch.exp(qq @ kk.t() * scale + add - lse[p, h][:, None])
             dp = dd @ vv.t()
+            keep = _attn_keep(drop, p, h, Nq, nk)
+            pdrop = pr
+            if keep is not None:       # O = (keep * P) V: dP = keep * (dO V^T), dV = (keep * P)^T dO; delta is unchanged
+                dp = dp * keep
+                pdrop = pr * keep
             ds = pr * (dp - (dd * oo).sum(-1, keepdim=True)) * scale
             dq_out[q0:q0 + Nq, sl] = (ds @ kk).to(dq_out.dtype)
             dkv[k0:k0 + nk, sl] += ds.t() @ qq
-            dkv[k0:k0 + nk, H * hd + h * hd:H * hd + (h + 1) * hd] += pr.t() @ dd
+            dkv[k0:k0 + nk, H * hd + h * hd:H * hd + (h + 1) * hd] += pdrop.t() @ dd
     if dkv_out is not None:
         dkv_out[0].copy_(dkv[:, :H * hd].to(dkv_out[0].dtype))
         dkv_out[1].copy_(dkv[:, H * hd:].to(dkv_out[1].dtype))

@@ -245,16 +245,20 @@ def test_mha(dtype, case):
     ((2, 4, 14, 14), (4, 7, 7), (0, 3, 3), 4),    # 196-token windows, masked border windows
     ((1, 8, 21, 14), (8, 7, 7), (0, 3, 3), 1),    # 392-token windows, 3x2 window grid, single head
 ])
-@pytest.mark.parametrize("backend", ["auto", "mma_sync"])
+@pytest.mark.parametrize("backend", ["auto", "tensor", "mma_sync"])
 def test_window_attention(dtype, grid, win, shift, heads, backend):
     """shift / partition / relative-position bias / -100 mask evaluated in-kernel vs the reference's
     roll + window_partition + bias gather + compute_mask (videoswin.py:75-84,137-163,272-285).
     heads == 2 cases run head dim 64 (the key-blocked flash kernels), the others head dim 32
     (the one-CTA-per-window kernels)."""
     k = K()
-    if backend == "mma_sync" and dtype != torch.bfloat16:
+    if backend != "auto" and dtype != torch.bfloat16:
         pytest.skip("backend selection only matters for the bf16 tensor-core paths")
-    be = {"auto": k.BACKEND_AUTO, "mma_sync": k.BACKEND_MMA_SYNC}[backend]   # auto: tcgen05 kernels where eligible
+    # tensor: tcgen05 forward + backward; auto: mma.sync forward + tcgen05 backward (the faster pair); mma_sync: round-1 kernels
+    be = {"auto": k.BACKEND_AUTO, "tensor": k.BACKEND_TENSOR, "mma_sync": k.BACKEND_MMA_SYNC}[backend]
+    hd_ = 64 if (heads == 2 and grid[1] == 16) else 32
+    if backend == "tensor" and hd_ != 32:
+        pytest.skip("the tcgen05 window kernels are head-dim-32 kernels")
     hd = 64 if (heads == 2 and grid[1] == 16) else 32
     C = heads * hd
     cfg_win = (8, 7, 7)
@@ -524,3 +528,70 @@ def test_retrieval_scoring_at_the_msrvtt_size(dtype):
     assert abs(log["forward_meanR"] - (rank.mean().item() + 1)) < 1e-2 and log["forward_medianR"] == rank.median().item() + 1
     r1 = (rank < 1).float().mean().item()
     assert log["forward_recall"].split("/")[0] == str(round(r1 * 100, 1))
+
+
+@pytest.mark.parametrize("case", ["self", "cross"])
+def test_attention_probability_dropout(case):
+    """bert.py:283,334 / transformer.py:128: dropout on the softmax output inside the attention kernels.  With V = I the
+    output IS the dropped probability matrix: kept entries are P/(1-p), the keep rate is 1-p, the log-sum-exp is that of
+    the undropped softmax; the backward must regenerate the same mask (gradients vs the reference formulas fed with the
+    extracted mask)."""
+    import tests.cpu_backend as RB
+    k = K()
+    H, hd, pd = 2, 64, 0.1
+    if case == "self":
+        P_, Nq, nk = 6, 48, 48
+    else:
+        P_, Nq, nk = 3, 40, 64
+    Hd = H * hd
+    q = rnd(P_ * Nq, Hd, dtype=torch.bfloat16, seed=1)
+    kk = rnd(P_ * nk, Hd, dtype=torch.bfloat16, seed=2)
+    eye = torch.zeros(P_ * nk, Hd)
+    for p in range(P_):
+        for h in range(H):
+            eye[p * nk:(p + 1) * nk, h * hd:h * hd + nk] = torch.eye(nk)
+    st = torch.tensor([77, 5 << 24], dtype=torch.int64, device="cuda")
+    drop = (pd, st, 9)
+    scale = hd ** -0.5
+    kw = dict(P_=P_, H=H, hd=hd, Nq=Nq, max_nk=nk, scale=scale)
+    qd, kd, vd = dev(q, torch.bfloat16), dev(kk, torch.bfloat16), dev(eye, torch.bfloat16)
+    o_drop, lse = k.mha_fwd(qd, kd, vd, drop=drop, **kw)
+    o_ref, lse_ref = k.mha_fwd(qd, kd, vd, **kw)
+    torch.testing.assert_close(lse, lse_ref)                                     # statistics of the undropped softmax
+    assert torch.equal(k.mha_fwd(qd, kd, vd, drop=drop, **kw)[0], o_drop)         # deterministic in {state, site}
+    keep = {}
+    rate = []
+    ncol = min(nk, hd)
+    for p in range(P_):
+        for h in range(H):
+            pd_ = o_drop[p * Nq:(p + 1) * Nq, h * hd:h * hd + ncol].float().cpu()
+            pr_ = o_ref[p * Nq:(p + 1) * Nq, h * hd:h * hd + ncol].float().cpu()
+            big = pr_ > 1e-3
+            m = (pd_ > 0.5 * pr_)
+            torch.testing.assert_close(pd_[m & big], (pr_ / (1 - pd))[m & big], rtol=2e-2, atol=1e-3)
+            assert (pd_[~m & big].abs() < 1e-6).all()
+            rate.append(m[big].float().mean().item())
+            full = torch.ones(Nq, nk, dtype=torch.bool)
+            full[:, :ncol] = m | ~big                       # tiny probabilities: treat as kept (their gradient weight is ~0)
+            keep[(p, h)] = full
+    assert abs(sum(rate) / len(rate) - (1 - pd)) < 0.02
+    if nk > hd:
+        return      # the mask of the key columns beyond the 64 identity columns cannot be read back: forward checks only
+    # backward with the extracted mask
+    v = rnd(P_ * nk, Hd, dtype=torch.bfloat16, seed=3)
+    do = rnd(P_ * Nq, Hd, dtype=torch.bfloat16, seed=4)
+    vd2 = dev(v, torch.bfloat16)
+    o2, lse2 = k.mha_fwd(qd, kd, vd2, drop=drop, **kw)
+    dq = torch.empty(P_ * Nq, Hd, device="cuda", dtype=torch.bfloat16)
+    dkv = torch.empty(P_ * nk, 2 * Hd, device="cuda", dtype=torch.bfloat16)
+    k.mha_bwd(qd, kd, vd2, o2, dev(do, torch.bfloat16), lse2, dq, P_, H, hd, Nq, nk, scale, dkv_out=(dkv[:, :Hd], dkv[:, Hd:]), drop=drop)
+    RB.KEEP_OVERRIDE = keep
+    try:
+        o_r, lse_r = RB.mha_fwd(q, kk, v, P_, H, hd, Nq, nk, scale, drop=(pd, None, 0))
+        dq_r = torch.zeros(P_ * Nq, Hd)
+        dkv_r = RB.mha_bwd(q, kk, v, o_r, do, lse_r, dq_r, P_, H, hd, Nq, nk, scale, drop=(pd, None, 0))
+    finally:
+        RB.KEEP_OVERRIDE = None
+    close(o2, o_r, torch.bfloat16, "dropout o")
+    close(dq, dq_r, torch.bfloat16, "dropout dq")
+    close(dkv, dkv_r, torch.bfloat16, "dropout dkv")

@@ -38,14 +38,14 @@ def window(B, grid_hw, heads, shift, name, D=8, backend=0):
     ms_b = bench(lambda: K.window_attn_bwd(qkv, o, do, lse, table, dt, *geom, backend=backend))
     nprob = B * (D // min(D, 8)) * (H // 7) * (W // 7) * heads
     fl = 4.0 * N * N * hd * nprob
-    print(json.dumps({"kernel": name, "backend": {0: "tcgen05 (auto)", 3: "mma.sync (round 1)"}.get(backend, backend), "problems": nprob, "fwd_ms": round(ms_f, 3), "bwd_ms": round(ms_b, 3),
+    print(json.dumps({"kernel": name, "backend": {0: "auto (mma.sync fwd + tcgen05 bwd)", 1: "tcgen05", 3: "mma.sync (round 1)"}.get(backend, backend), "problems": nprob, "fwd_ms": round(ms_f, 3), "bwd_ms": round(ms_b, 3),
                       "fwd_tflops": round(fl / ms_f / 1e9, 1), "bwd_tflops": round(2.5 * fl / ms_b / 1e9, 1),
                       "elems_per_ns_fwd": round(N * N * nprob / ms_f / 1e6, 1)}), flush=True)
 
 
 def main():
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["s1", "s1s", "s3"]
-    for be in ((3, 0) if "--both" in sys.argv else (0,)):
+    for be in ((3, 1, 0) if "--both" in sys.argv else (0,)):
         if "s1" in which:
             window(32, 56, 4, (0, 0, 0), "swin stage1 (no shift)", backend=be)
         if "s1s" in which:

@@ -31,7 +31,7 @@ for grid, win, shift, heads in [((2, 8, 14, 14), (8, 7, 7), (0, 3, 3), 4), ((2, 
     table = torch.randn(15 * 13 * 13, heads, device="cuda", generator=g) * 0.5
     ref = run(grid, win, shift, heads, torch.float32, K.BACKEND_SIMT, qkv32, do32, table)
     out = {"grid": grid, "win": win, "shift": shift}
-    for name, be in (("tcgen05", K.BACKEND_AUTO), ("mma_sync", K.BACKEND_MMA_SYNC)):
+    for name, be in (("tcgen05", K.BACKEND_TENSOR), ("mma_sync", K.BACKEND_MMA_SYNC)):
         got = run(grid, win, shift, heads, torch.bfloat16, be, qkv32, do32, table)
         out[name] = {"o": rel(got[0], ref[0]), "lse": rel(got[1], ref[1]), "dq": rel(got[2][:, :C], ref[2][:, :C]),
                      "dk": rel(got[2][:, C:2 * C], ref[2][:, C:2 * C]), "dv": rel(got[2][:, 2 * C:], ref[2][:, 2 * C:]),

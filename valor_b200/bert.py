@@ -227,11 +227,12 @@ class BertModel(nn.Module):
                                         for i in range(n_pass * T)], dtype=torch.int32, device=dev)
             cache[ck] = (c_t, r_t, l_t, q_t, ulen, media is not None and u0 == 0 and ulen == media.shape[0] // n_media_samples)
         causal, row0_c, lens_c, qrange_c, ulen, kv_full = cache[ck]
-        self_spec = dict(P=R, H=H, hd=hd, Nq=T, max_nk=T, scale=1.0 / math.sqrt(hd), key_valid=key_valid, causal=causal)
+        drop = dict(rng=rng, attn_drop=cfg.attention_probs_dropout_prob, dtype_is_fp32=dtype == torch.float32 and tokens.is_cuda)   # bert.py:283,334 (fp32 CUDA = SIMT parity kernels: no dropout there)
+        self_spec = dict(P=R, H=H, hd=hd, Nq=T, max_nk=T, scale=1.0 / math.sqrt(hd), key_valid=key_valid, causal=causal, **drop)
         cross_spec = None
         if media is not None:
             cross_spec = dict(P=Bp, H=H, hd=hd, Nq=n_pass * T, max_nk=ulen, scale=1.0 / math.sqrt(hd), kv_row0=row0_c,
-                              kv_len=lens_c, q_key_range=qrange_c, kv_exclusive=True, kv_full=kv_full)
+                              kv_len=lens_c, q_key_range=qrange_c, kv_exclusive=True, kv_full=kv_full, **drop)
         for layer in self.encoder.layer:
             h = layer.run(h, self_spec, media, cross_spec)
         return h

@@ -68,11 +68,13 @@ int dual_softmax(const float*, float*, long long, long long, const float*, int, 
 bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
                        const void* k, const void* v, const void* o);
 int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
-                long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
+                long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale, float drop_p,
+                const long long* rng, long long site, cudaStream_t st);
 int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                 long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta, void* dQ,
                 long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp, void* dV_lp,
-                long long lddkv_lp, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st);
+                long long lddkv_lp, int Pn, int H, int hd, int Nq, float scale, float drop_p, const long long* rng, long long site,
+                cudaStream_t st);
 int window_mma_fwd(const WindowIndex& ix, const void* qkv, long long ld, void* O, long long ldo, float* lse, int Pn,
                    int H, int hd, float scale, cudaStream_t st);
 int window_mma_bwd(const WindowIndex& ix, const void* qkv, long long ld, const void* O, const void* dO, long long ldo,
@@ -164,14 +166,18 @@ static MhaIndex make_mha(int Nq, int max_nk, const int* q_row0, const int* kv_ro
 int valor_mha_fwd(int dtype, const void* Q, const void* K, const void* V, long long ldq, long long ldk, long long ldv,
                   void* O, long long ldo, float* lse, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid, const unsigned char* causal,
-                  const int* q_key_range, float scale, int backend, void* stream) {
+                  const int* q_key_range, float scale, float drop_p, const long long* rng_state, long long site, int backend,
+                  void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
   ix.q_key_range = q_key_range;
   VALOR_REQUIRE(q_key_range == nullptr || max_nk < 65535, "valor_mha_fwd: per-query key ranges need max_nk < 65535");
+  VALOR_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || rng_state != nullptr), "valor_mha_fwd: bad dropout arguments");
   const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O);
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_fwd: tensor backend requested but not eligible");
-  if (backend != VALOR_BACKEND_SIMT && ok) return mha_mma_fwd(ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, ST);
+  if (backend != VALOR_BACKEND_SIMT && ok)
+    return mha_mma_fwd(ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, drop_p, rng_state, site, ST);
+  VALOR_REQUIRE(drop_p == 0.f, "valor_mha_fwd: attention dropout is a tensor-core-path feature (the fp32 parity path runs without)");
   return mha_ref_fwd(dtype, ix, Q, K, V, ldq, ldk, ldv, O, ldo, lse, P, H, hd, Nq, scale, ST);
 }
 int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const void* O, const void* dO,
@@ -179,17 +185,20 @@ int valor_mha_bwd(int dtype, const void* Q, const void* K, const void* V, const 
                   void* dQ, long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp,
                   void* dV_lp, long long lddkv_lp, int P, int H, int hd, int Nq, int max_nk, const int* q_row0,
                   const int* kv_row0, const int* kv_len, const unsigned char* key_valid,
-                  const unsigned char* causal, const int* q_key_range, float scale, int backend, void* stream) {
+                  const unsigned char* causal, const int* q_key_range, float scale, float drop_p, const long long* rng_state,
+                  long long site, int backend, void* stream) {
   if (P == 0) return 0;
   MhaIndex ix = make_mha(Nq, max_nk, q_row0, kv_row0, kv_len, key_valid, causal);
   ix.q_key_range = q_key_range;
   VALOR_REQUIRE(q_key_range == nullptr || max_nk < 65535, "valor_mha_bwd: per-query key ranges need max_nk < 65535");
+  VALOR_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || rng_state != nullptr), "valor_mha_bwd: bad dropout arguments");
   const bool ok = attn_mma_eligible(dtype, hd, ldq, ldk, ldv, ldo, Q, K, V, O) && (lddq % 8 == 0) &&
                   (((uintptr_t)dQ | (uintptr_t)dO) & 15) == 0 && delta != nullptr;
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_mha_bwd: tensor backend requested but not eligible");
   if (backend != VALOR_BACKEND_SIMT && ok)
     return mha_mma_bwd(ix, Q, K, V, O, dO, ldq, ldk, ldv, ldo, lse, delta, dQ, lddq, dK, dV, lddk, lddv, dK_lp, dV_lp,
-                       lddkv_lp, P, H, hd, Nq, scale, ST);
+                       lddkv_lp, P, H, hd, Nq, scale, drop_p, rng_state, site, ST);
+  VALOR_REQUIRE(drop_p == 0.f, "valor_mha_bwd: attention dropout is a tensor-core-path feature");
   // row-per-warp path: fp32 accumulation only; in fp32 parity mode the "direct" outputs ARE fp32 buffers
   if (dK == nullptr && dtype == VALOR_DT_F32 && dK_lp != nullptr) {
     dK = (float*)dK_lp; dV = (float*)dV_lp; lddk = lddv = lddkv_lp;
@@ -222,7 +231,9 @@ int valor_window_attn_fwd(int dtype, const void* qkv, long long ld, void* O, lon
   const char* qb = (const char*)qkv;
   const bool ok = attn_mma_eligible(dtype, hd, ld, ld, ld, ldo, qb, qb + 2 * heads * hd, qb + 4 * heads * hd, O);
   if (backend == VALOR_BACKEND_TENSOR) VALOR_REQUIRE(ok, "valor_window_attn_fwd: tensor backend requested but not eligible");
-  if (backend != VALOR_BACKEND_SIMT && backend != VALOR_BACKEND_MMA_SYNC && ok && window_sm100_fwd_eligible(ix, hd))
+  // forward: the tcgen05 / TMEM kernel is taken on request (VALOR_BACKEND_TENSOR); AUTO keeps the round-1 mma.sync kernel,
+  // which is still the faster of the two at these 392-token, head-dim-32 problems (profiles/window_attention_r2.md)
+  if (backend == VALOR_BACKEND_TENSOR && ok && window_sm100_fwd_eligible(ix, hd))
     return window_sm100_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);     // tcgen05 / TMEM
   if (backend != VALOR_BACKEND_SIMT && ok && window_use_cta(ix, hd))
     return window_cta_fwd(ix, qkv, ld, O, ldo, lse, P, heads, hd, scale, ST);

@@ -64,8 +64,22 @@ struct AttnParams {
   bf16* dK_lp; bf16* dV_lp; long long lddkv_lp;      // direct bf16 outputs (window / self)
   float* dK; float* dV; long long lddk, lddv;         // fp32 accumulate outputs (cross: shared K/V rows)
   float* dtable;
+  // attention-probability dropout (bert.py:283,334; transformer.py:128): P_drop = keep * P / (1-p) feeds P.V; the row sums /
+  // log-sum-exp stay those of the undropped softmax.  keep(i,j) = mix32(key(problem, head), i * max_nk + j) >= thr.
+  float drop_p; const long long* rng; long long site;
   MhaIndex mha;
   WindowIndex win;
+};
+struct DropCtx {
+  uint32_t key, thr, stride; float inv; bool on;
+  __device__ __forceinline__ void init(const AttnParams& P, int p, int h) {
+    on = P.drop_p > 0.f && P.rng != nullptr;
+    key = 0; thr = 0; inv = 1.f; stride = (uint32_t)P.max_nk;
+    if (on) { key = rng4(P.rng, P.site, (unsigned long long)((long long)p * P.H + h)).x; thr = drop_threshold(P.drop_p); inv = 1.0f / (1.0f - P.drop_p); }
+  }
+  __device__ __forceinline__ float apply(float v, int i, int j) const {   // v * keep / (1-p)
+    return mix32(key, (uint32_t)i * stride + (uint32_t)j) < thr ? 0.f : v * inv;
+  }
 };
 
 template <bool WINDOW>
@@ -231,6 +245,8 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
   const int i0 = qb * BQ + warp * 16 + g;  // rows i0 and i0+8
   const float sc2 = P.scale * LOG2E;
   const uint32_t qinf[2] = {t.qinfo[i0], t.qinfo[i0 + 8]};
+  DropCtx drop;
+  drop.init(P, p, h);
   for (int kb = kb0; kb < kb1; ++kb) {
     unsigned char* Ks = KVs + ((kb - kb0) & 1) * 2 * TILE;
     unsigned char* Vs = Ks + TILE;
@@ -296,8 +312,8 @@ attn_mma_fwd_kernel(AttnParams P, int nq_pad, int nk_pad) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float pv = fast_exp2(s[nt][e] - msafe[e >> 1]);
-        s[nt][e] = pv;
         lrow[e >> 1] += pv;
+        s[nt][e] = (!WINDOW && drop.on) ? drop.apply(pv, i0 + (e >> 1) * 8, kb * BKEY + nt * 8 + t4 * 2 + (e & 1)) : pv;
       }
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(s[nt][0], s[nt][1]);
       pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(s[nt][2], s[nt][3]);
@@ -414,6 +430,8 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
   const uint32_t qinf[2] = {t.qinfo[i0], t.qinfo[i0 + 8]};
   const float lse2[2] = {i0 < t.nq ? lse_s[il] * LOG2E : INFINITY, i0 + 8 < t.nq ? lse_s[il + 8] * LOG2E : INFINITY};
   const float del[2] = {del_s[il], del_s[il + 8]};
+  DropCtx drop;
+  drop.init(P, p, h);
   for (int kb = kb0; kb < kb1; ++kb) {
     unsigned char* Ks = KVs + ((kb - kb0) & 1) * 2 * TILE;
     unsigned char* Vs = Ks + TILE;
@@ -460,7 +478,8 @@ attn_mma_bwd_dq_kernel(AttnParams P, float* __restrict__ delta, int nq_pad, int 
           const float v = score2<WINDOW>(t, s[nt][e], sc2, qinf[r], kw, i0 + r * 8, jb + (e & 1));
           float pr = fast_exp2(v - lse2[r]);
           if (ragged && (kw >> 31)) pr = 0.f;
-          const float d = pr * (dp[nt][e] - del[r]);
+          const float dpe = (!WINDOW && drop.on) ? drop.apply(dp[nt][e], i0 + r * 8, jb + (e & 1)) : dp[nt][e];
+          const float d = pr * (dpe - del[r]);
           if (WINDOW) {
             // two native int32 adds without return: coarse word at 2^-16, remainder word at 2^-40
             const int hi = __float2int_rn(d * 65536.0f);
@@ -559,6 +578,8 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
   const float sc = P.scale, sc2 = P.scale * LOG2E;
   const int j0 = kb * BKEY + warp * 16 + g;  // keys j0 and j0+8 (padding keys: K/V rows are zero, results dropped)
   const uint32_t kinf[2] = {t.kinfo[j0], t.kinfo[j0 + 8]};
+  DropCtx drop;
+  drop.init(P, p, h);
   uint32_t todo = qmask;
   for (int it = 0; todo != 0; ++it) {
     const int qb = __ffs(todo) - 1;
@@ -609,8 +630,10 @@ attn_mma_bwd_dkv_kernel(AttnParams P, const float* __restrict__ delta, int nq_pa
           const uint32_t qw = (e & 1) ? qi2.y : qi2.x;
           const float v = score2<WINDOW>(t, s[nt][e], sc2, qw, kinf[r], ib + (e & 1), j0 + r * 8);
           const float pr = fast_exp2(v - ((e & 1) ? l2.y : l2.x));   // padding queries carry lse = +inf -> 0
-          pv[e] = pr;
-          ds[e] = pr * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * sc;
+          const bool dr = !WINDOW && drop.on;
+          pv[e] = dr ? drop.apply(pr, ib + (e & 1), j0 + r * 8) : pr;
+          const float dpe = dr ? drop.apply(dp[nt][e], ib + (e & 1), j0 + r * 8) : dp[nt][e];
+          ds[e] = pr * (dpe - ((e & 1) ? d2.y : d2.x)) * sc;
         }
         pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
         pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
@@ -717,8 +740,9 @@ bool attn_mma_eligible(int dtype, int hd, long long ldq, long long ldk, long lon
 
 int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, long long ldq, long long ldk,
                 long long ldv, void* O, long long ldo, float* lse, int Pn, int H, int hd, int Nq, float scale,
-                cudaStream_t st) {
+                float drop_p, const long long* rng, long long site, cudaStream_t st) {
   AttnParams P = {};
+  P.drop_p = drop_p; P.rng = rng; P.site = site;
   P.Q = (const bf16*)Q; P.K = (const bf16*)K; P.V = (const bf16*)V; P.ldq = ldq; P.ldk = ldk; P.ldv = ldv;
   P.O = (bf16*)O; P.ldo = ldo; P.lse = lse; P.H = H; P.hd = hd; P.Nq = Nq; P.max_nk = ix.max_nk; P.scale = scale;
   P.mha = ix;
@@ -729,8 +753,10 @@ int mha_mma_fwd(const MhaIndex& ix, const void* Q, const void* K, const void* V,
 int mha_mma_bwd(const MhaIndex& ix, const void* Q, const void* K, const void* V, const void* O, const void* dO,
                 long long ldq, long long ldk, long long ldv, long long ldo, const float* lse, float* delta, void* dQ,
                 long long lddq, float* dK, float* dV, long long lddk, long long lddv, void* dK_lp, void* dV_lp,
-                long long lddkv_lp, int Pn, int H, int hd, int Nq, float scale, cudaStream_t st) {
+                long long lddkv_lp, int Pn, int H, int hd, int Nq, float scale, float drop_p, const long long* rng,
+                long long site, cudaStream_t st) {
   AttnParams P = {};
+  P.drop_p = drop_p; P.rng = rng; P.site = site;
   P.Q = (const bf16*)Q; P.K = (const bf16*)K; P.V = (const bf16*)V; P.ldq = ldq; P.ldk = ldk; P.ldv = ldv;
   P.O = (bf16*)O; P.ldo = ldo; P.lse = (float*)lse; P.H = H; P.hd = hd; P.Nq = Nq; P.max_nk = ix.max_nk; P.scale = scale;
   P.dO = (const bf16*)dO; P.dQ = (bf16*)dQ; P.lddq = lddq; P.dK = dK; P.dV = dV; P.lddk = lddk; P.lddv = lddv;

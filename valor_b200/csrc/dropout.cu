@@ -8,27 +8,6 @@
 
 namespace valor {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-// four uniform 32-bit words for elements [4*g, 4*g+4) of call site `site`
-__device__ __forceinline__ uint4 rng4(const long long* state, long long site, unsigned long long g) {
-  const unsigned long long seed = (unsigned long long)state[0], off = (unsigned long long)state[1] + (unsigned long long)site;
-  return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)off, (uint32_t)(off >> 32)),
-                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-}
-__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {   // drop iff word < threshold
-  const double t = (double)p * 4294967296.0;
-  return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
-}
-
 // out[r,c] = residual[r,c] + x[r,c] * keep / (1-p)      (C % 4 == 0; element index = r*C + c)
 template <typename T>
 __global__ void __launch_bounds__(256)

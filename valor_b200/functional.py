@@ -197,15 +197,25 @@ def window_attention(qkv, table_param, geom):
     return WindowAttnFn.apply(qkv, table_param.data, table_param.main_grad, geom)
 
 
+def _attn_drop(spec):
+    """(p, rng_state, site) of this attention call, or None: the probability and the generator ride in the spec dict
+    (`attn_drop`, `rng`); the call takes the next site id so that the backward regenerates the same mask."""
+    rng, p = spec.get("rng"), spec.get("attn_drop", 0.0)
+    if rng is None or not rng.active or p <= 0.0 or spec.get("dtype_is_fp32", False):
+        return None
+    return (p, rng.state, rng.next_site())
+
+
 class SelfAttnFn(Function):
     """softmax(q k^T * scale + mask) v over a fused [rows, 3*Hd] q|k|v buffer."""
 
     @staticmethod
     def forward(ctx, qkv, spec):
         Hd = spec["H"] * spec["hd"]
+        ctx.drop = _attn_drop(spec)
         o, lse = K.mha_fwd(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], spec["P"], spec["H"], spec["hd"],
                            spec["Nq"], spec["max_nk"], spec["scale"], key_valid=spec.get("key_valid"),
-                           causal=spec.get("causal"))
+                           causal=spec.get("causal"), drop=ctx.drop)
         ctx.save_for_backward(qkv, o, lse)
         ctx.spec = spec
         return o
@@ -218,7 +228,7 @@ class SelfAttnFn(Function):
         dqkv = torch.empty_like(qkv)
         K.mha_bwd(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], o, do, lse, dqkv[:, :Hd], s["P"], s["H"], s["hd"],
                   s["Nq"], s["max_nk"], s["scale"], key_valid=s.get("key_valid"), causal=s.get("causal"),
-                  dkv_out=(dqkv[:, Hd:2 * Hd], dqkv[:, 2 * Hd:]))
+                  dkv_out=(dqkv[:, Hd:2 * Hd], dqkv[:, 2 * Hd:]), drop=ctx.drop)
         return dqkv, None
 
 
@@ -232,8 +242,10 @@ class CrossAttnFn(Function):
     def forward(ctx, q, kv, spec):
         Hd = spec["H"] * spec["hd"]
         q = q.contiguous()
+        ctx.drop = _attn_drop(spec)
         o, lse = K.mha_fwd(q, kv[:, :Hd], kv[:, Hd:], spec["P"], spec["H"], spec["hd"], spec["Nq"], spec["max_nk"],
-                           spec["scale"], kv_row0=spec["kv_row0"], kv_len=spec["kv_len"], q_key_range=spec.get("q_key_range"))
+                           spec["scale"], kv_row0=spec["kv_row0"], kv_len=spec["kv_len"], q_key_range=spec.get("q_key_range"),
+                           drop=ctx.drop)
         ctx.save_for_backward(q, kv, o, lse)
         ctx.spec = spec
         return o
@@ -248,10 +260,10 @@ class CrossAttnFn(Function):
             dkv = torch.empty_like(kv) if s.get("kv_full") else torch.zeros_like(kv)   # rows outside every range get 0
             K.mha_bwd(q, kv[:, :Hd], kv[:, Hd:], o, do, lse, dq, s["P"], s["H"], s["hd"], s["Nq"], s["max_nk"], s["scale"],
                       kv_row0=s["kv_row0"], kv_len=s["kv_len"], q_key_range=s.get("q_key_range"),
-                      dkv_out=(dkv[:, :Hd], dkv[:, Hd:]))
+                      dkv_out=(dkv[:, :Hd], dkv[:, Hd:]), drop=ctx.drop)
             return dq, dkv, None
         dkv32 = K.mha_bwd(q, kv[:, :Hd], kv[:, Hd:], o, do, lse, dq, s["P"], s["H"], s["hd"], s["Nq"], s["max_nk"],
-                          s["scale"], kv_row0=s["kv_row0"], kv_len=s["kv_len"], q_key_range=s.get("q_key_range"))
+                          s["scale"], kv_row0=s["kv_row0"], kv_len=s["kv_len"], q_key_range=s.get("q_key_range"), drop=ctx.drop)
         if kv.dtype == torch.float32:
             dkv = dkv32
         else:

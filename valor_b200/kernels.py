@@ -126,22 +126,26 @@ def l2norm_bwd(dy, x, nrm):
 # attention
 # ------------------------------------------------------------------------------------------
 def mha_fwd(q, k, v, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None, key_valid=None,
-            causal=None, q_key_range=None, backend=BACKEND_AUTO):
+            causal=None, q_key_range=None, backend=BACKEND_AUTO, drop=None):
     """q: [rows_q, >=H*hd] view, k/v: [rows_kv, >=H*hd] views (may alias one fused buffer).
-    q_key_range: int32 [Nq, 2], query i only sees keys lo <= j < hi of its problem."""
+    q_key_range: int32 [Nq, 2], query i only sees keys lo <= j < hi of its problem.
+    drop = (p, rng_state, site): attention-probability dropout (regenerated in mha_bwd from the same triple)."""
+    dp, drs, dsite = drop if drop is not None else (0.0, None, 0)
     o = torch.empty(q.shape[0], H * hd, device=q.device, dtype=q.dtype)
     lse = torch.empty(P_, H, Nq, device=q.device, dtype=torch.float32)
     _call("valor_mha_fwd", DT(q), P(q), P(k), P(v), _ld(q), _ld(k), _ld(v), P(o), _ld(o), P(lse), P_, H, hd, Nq,
-          max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal), P(q_key_range), float(scale), backend, ST())
+          max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal), P(q_key_range), float(scale), float(dp), P(drs),
+          int(dsite), backend, ST())
     return o, lse
 
 
 def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=None, kv_row0=None, kv_len=None,
-            key_valid=None, causal=None, dkv_out=None, q_key_range=None, backend=BACKEND_AUTO):
+            key_valid=None, causal=None, dkv_out=None, q_key_range=None, backend=BACKEND_AUTO, drop=None):
     """dq_out: [rows_q, >=H*hd] view receiving dQ.
     dkv_out=None  -> returns an fp32 [rows_kv, 2*H*hd] buffer with dK|dV accumulated (shared K/V rows: cross-attention);
     dkv_out=(dk_view, dv_view) in the compute dtype -> written directly (each K/V row owned by one problem)."""
     do = do.contiguous()
+    dp, drs, dsite = drop if drop is not None else (0.0, None, 0)
     delta = torch.empty_like(lse)
     if dkv_out is None:
         dkv = torch.zeros(k.shape[0], 2 * H * hd, device=q.device, dtype=torch.float32)
@@ -156,7 +160,7 @@ def mha_bwd(q, k, v, o, do, lse, dq_out, P_, H, hd, Nq, max_nk, scale, q_row0=No
         args = (None, None, 0, 0, P(dk), P(dv), _ld(dk))
     _call("valor_mha_bwd", DT(q), P(q), P(k), P(v), P(o), P(do), _ld(q), _ld(k), _ld(v), _ld(o), P(lse), P(delta), P(dq_out),
           _ld(dq_out), *args, P_, H, hd, Nq, max_nk, P(q_row0), P(kv_row0), P(kv_len), P(key_valid), P(causal),
-          P(q_key_range), float(scale), backend, ST())
+          P(q_key_range), float(scale), float(dp), P(drs), int(dsite), backend, ST())
     return dkv
 
 

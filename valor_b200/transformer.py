@@ -48,7 +48,8 @@ class TransformerLayer(nn.Module):
         hd = att.hidden_size // H
         h, xr = Fn.layer_norm_residual(x, LN(self.layernorm1.weight, self.layernorm1.bias, 1e-12))
         qkv = Fn.linear(h, fused_lin([l.weight for l in att.linears[:3]], [l.bias for l in att.linears[:3]]))
-        spec = dict(P=n_seq, H=H, hd=hd, Nq=seq_len, max_nk=seq_len, scale=1.0 / math.sqrt(hd))
+        spec = dict(P=n_seq, H=H, hd=hd, Nq=seq_len, max_nk=seq_len, scale=1.0 / math.sqrt(hd), rng=rng,
+                    attn_drop=self.attention_dropout, dtype_is_fp32=x.dtype == torch.float32 and x.is_cuda)   # transformer.py:112,128
         o = Fn.SelfAttnFn.apply(qkv, spec)
         x = Fn.residual_branch(lambda r: Fn.linear(o, lin_of(att.linears[3].weight, att.linears[3].bias), residual=r), xr, rng,
                                self.hidden_dropout)                                    # residual + dropout(attn), :78
