@@ -60,6 +60,9 @@ typedef struct ValorGemmEpilogue {
   int out_dtype;
   int accumulate; /* C += (fp32 C only); required for split-K */
   float alpha;
+  float* bias_grad; /* NULL, or (a_kmajor = b_kmajor = 0, accumulate = 1: the weight-gradient form dW += dy^T x):
+                       bias_grad[m] += alpha * sum_k A[k,m], i.e. the bias gradient torch autograd produces for nn.Linear,
+                       fused into the same launch (no second pass over dy) */
 } ValorGemmEpilogue;
 
 int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor,

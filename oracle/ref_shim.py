@@ -106,9 +106,9 @@ def reference_env(swin_sd, ast_sd, bert_sd, bert_config):
         sys.path.insert(0, REFERENCE_ROOT)
     import torch.distributed as dist
     if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29517")
-        dist.init_process_group("gloo", rank=0, world_size=1)
+        # single-process group over a file store: no TCP port, so a pytest parent and a probe subprocess never collide
+        store_file = os.path.join(tempfile.mkdtemp(prefix="valor_ref_pg_"), "store")
+        dist.init_process_group("gloo", init_method=f"file://{store_file}", rank=0, world_size=1)
     old_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     old_load = torch.load

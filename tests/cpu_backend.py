@@ -39,8 +39,10 @@ def _act_grad(x, act):
 
 def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residual=None, act_aux=None,
          want_preact=False, out=None, out_dtype=None, accumulate=False, alpha=1.0, backend=0, force_bn=0,
-         force_splits=0):
+         force_splits=0, bias_grad=None):
     A = a.float() if a_kmajor else a.float().t()
+    if bias_grad is not None:
+        bias_grad += alpha * A.sum(1)
     Bm = b.float() if b_kmajor else b.float().t()
     x = alpha * (A @ Bm.t())
     if bias is not None:

@@ -111,6 +111,26 @@ def test_gemm_wgrad_accumulate_splitk(dtype):
     close(out, ref, dtype, "wgrad split-K")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(20000, 384, 128, 0), (25088, 768, 768, 0), (3000, 3072, 768, 0), (777, 200, 72, 0),
+                                   (6000, 30522, 768, 0), (4096, 512, 512, 128), (4096, 512, 512, 64)])
+def test_gemm_wgrad_fused_bias_gradient(dtype, shape):
+    """Linear backward: dW += dY^T X and db += column sums of dY from ONE launch (the bias gradient rides on sixteen
+    extra accumulator columns fed by an all-ones operand); fp32 operands take the separate column-sum launch behind the
+    same call.  Both accumulate into existing buffers."""
+    k = K()
+    Mrows, N, Kin, bn = shape
+    dy, x = rnd(Mrows, N, dtype=dtype, seed=20, scale=0.1), rnd(Mrows, Kin, dtype=dtype, seed=21)
+    base_w, base_b = rnd(N, Kin, seed=22), rnd(N, seed=23)
+    out, db = dev(base_w.clone()), dev(base_b.clone())
+    kw = dict(force_bn=bn, backend=k.BACKEND_TENSOR) if (bn and dtype == torch.bfloat16) else {}
+    k.gemm(dev(dy, dtype), dev(x, dtype), a_kmajor=False, b_kmajor=False, out=out, accumulate=True, bias_grad=db, **kw)
+    close(out, base_w + dy.t() @ x, dtype, "wgrad with fused bias gradient")
+    ref_b = base_b.double() + dy.double().sum(0)
+    err = (db.cpu().double() - ref_b).abs().max().item()
+    assert err <= 1e-4 * (1.0 + dy.abs().double().sum(0).max().item()), f"bias gradient max abs err {err}"
+
+
 def test_gemm_padded_pitch_vocab():
     """30522-wide logits with a row pitch padded to 30528 (MLM decoder, modeling.py:240-253)."""
     k = K()

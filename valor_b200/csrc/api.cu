@@ -27,6 +27,7 @@ int check_launch(const char* what) {
 bool gemm_sm100_eligible(const void* A, const void* B, long long lda, long long ldb, int M, int N, int K);
 int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor, void* C,
                long long ldc, int M, int N, int K, const GemmEpilogue& ep, int force_bn, int force_splits, cudaStream_t st);
+bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor);
 int gemm_simt(int dtype, const void* A, long long sam, long long sak, const void* B, long long sbn, long long sbk,
               void* C, long long ldc, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st);
 int layernorm_fwd(int, const void*, const float*, const float*, void*, float*, float*, long long, int, float, cudaStream_t);
@@ -125,7 +126,8 @@ int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void
   ep.bias = epc->bias; ep.residual = epc->residual; ep.act_aux = epc->act_aux; ep.preact_out = epc->preact_out;
   ep.ldr = epc->ldr; ep.ld_aux = epc->ld_aux; ep.ld_pre = epc->ld_pre;
   ep.res_dtype = epc->res_dtype; ep.aux_dtype = epc->aux_dtype; ep.act = epc->act; ep.out_dtype = epc->out_dtype;
-  ep.accumulate = epc->accumulate; ep.alpha = epc->alpha;
+  ep.accumulate = epc->accumulate; ep.alpha = epc->alpha; ep.bias_grad = epc->bias_grad;
+  VALOR_REQUIRE(ep.bias_grad == nullptr || (!a_kmajor && !b_kmajor && ep.accumulate), "valor_gemm: bias_grad needs the weight-gradient form (a_kmajor = b_kmajor = 0, accumulate = 1)");
   bool tensor_ok = dtype == VALOR_DT_BF16 && gemm_sm100_eligible(A, B, lda, ldb, M, N, K) &&
                    (ep.residual == nullptr || ep.res_dtype == VALOR_DT_BF16) &&
                    (ep.act_aux == nullptr || ep.aux_dtype == VALOR_DT_BF16) &&
@@ -133,7 +135,14 @@ int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void
                    (!ep.accumulate || ep.out_dtype == VALOR_DT_F32);
   if (backend == VALOR_BACKEND_TENSOR)
     VALOR_REQUIRE(tensor_ok, "valor_gemm: tensor backend requested but operands are not eligible");
-  if (backend == VALOR_BACKEND_TENSOR || (backend == VALOR_BACKEND_AUTO && tensor_ok))
+  const bool use_tensor = backend == VALOR_BACKEND_TENSOR || (backend == VALOR_BACKEND_AUTO && tensor_ok);
+  if (ep.bias_grad != nullptr && !(use_tensor && gemm_sm100_fuses_bias_grad(C, ldc, ep, a_kmajor, b_kmajor))) {
+    // not fusable here (fp32 operands / odd pitches): the bias gradient is its own column-sum launch over A = dY [K, M]
+    VALOR_REQUIRE(ep.alpha == 1.f, "valor_gemm: unfused bias_grad needs alpha = 1");
+    if (colsum(dtype, A, lda, ep.bias_grad, K, M, ST)) return 1;
+    ep.bias_grad = nullptr;
+  }
+  if (use_tensor)
     return gemm_sm100(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, ep, force_bn, force_splits, ST);
   return gemm_simt(dtype, A, a_kmajor ? lda : 1, a_kmajor ? 1 : lda, B, b_kmajor ? ldb : 1, b_kmajor ? 1 : ldb, C, ldc,
                    M, N, K, ep, ST);

@@ -193,6 +193,8 @@ struct GemmEpilogue {
   int out_dtype;         // VALOR_DT_*
   int accumulate;        // 1: C += result (fp32 out only; atomic when split-K)
   float alpha;           // scales the accumulator before bias
+  float* bias_grad;      // wgrad form only ([K,M] x [K,N] operands): bias_grad[m] += alpha * sum_k A[k,m]  (the Linear's bias
+                         // gradient = column sums of dy), taken from a ones-column MMA on the A tiles already in shared memory
 };
 
 }  // namespace valor

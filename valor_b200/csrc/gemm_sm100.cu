@@ -192,27 +192,33 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
   }
 }
 
-template <int BLOCK_N>
+// BG: the weight-gradient launch also produces the bias gradient (row sums of A over the contraction) through one extra
+// N = 16 MMA per k-step against a constant all-ones B tile: 8 KB of shared memory, 16 more accumulator columns per stage.
+template <int BLOCK_N, bool BG = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 4 * 16384;  // per epilogue half: 128x64 bf16 out tile + pre-activation tile
   static constexpr int BIAS_BYTES = 4096;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - BIAS_BYTES - STAGING_BYTES;
+  static constexpr int ONES_BYTES = BG ? 768 + 2048 : 0;   // pad to 1 KB + [16 rows][64 k] of bf16 1.0 (K-major B operand)
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - BIAS_BYTES - STAGING_BYTES - ONES_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES;
+  static constexpr int ACC_COLS = 2 * BLOCK_N + (BG ? 32 : 0);
+  static constexpr int TMEM_COLS = (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256 ? 256 : 512);
+  static_assert(ACC_COLS <= 512, "accumulators do not fit tensor memory");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES + ONES_BYTES;
 };
 
-template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR, int MODE>
+template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR, int MODE, bool BG = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                   void* __restrict__ Cptr, long long ldc, int M, int N, int K, int k_splits, int vec_ok,
                   int tma_store, int dbg, GemmEpilogue ep) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, BG>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!BG || (MODE == EPI_ACC && !A_KMAJOR && !B_KMAJOR), "bias-gradient fusion belongs to the weight-gradient form");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -225,6 +231,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
   float* bias_s = (float*)(staging + Cfg::STAGING_BYTES + 256);
+  uint8_t* ones_s = staging + Cfg::STAGING_BYTES + 256 + Cfg::BIAS_BYTES + 768;   // (BG) 1024-aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -250,6 +257,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 8; ++i) mbar_init(&bars[2 * STAGES + 6 + i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (BG) {   // all-ones B tile (every element equal: swizzle / layout cannot matter)
+    for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x) ((uint4*)ones_s)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
@@ -307,11 +318,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // bias-gradient MMA: A as above (MN-major), B = sixteen K-major rows of ones
+      const uint32_t idesc_bg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
+                                ((uint32_t)(BLOCK_M >> 4) << 24);
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int rest = w / n_blocks;
         const int ks = rest / m_blocks;
         const int kb0 = ks * kb_per;
         const int kb1 = min(kb0 + kb_per, kb_total);
+        const bool bg_tile = BG && (w % n_blocks) == 0;     // one column of tiles owns the row sums of A
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -329,6 +344,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t bdesc = B_KMAJOR ? make_smem_desc(sb + k * UMMA_K * 2, 0, 1024)
                                             : make_smem_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024);
             tcgen05_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (BG && bg_tile)   // bias gradient: the same A tile against sixteen columns of ones
+              tcgen05_mma_bf16(tmem_base + 2 * BLOCK_N + acc * 16, adesc,
+                               make_smem_desc(smem_u32(ones_s) + k * UMMA_K * 2, 0, 1024), idesc_bg,
+                               (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == kb1 - 1) tcgen05_commit(&tmem_full[acc]);
@@ -389,6 +408,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&tmem_full[acc], acc_phase);
           tcgen05_fence_after();
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+          if (BG && n_blk == 0 && half == 0) {   // row sums of A (bias gradient): every one of the 16 columns carries the sum
+            uint32_t vb8[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(vb8[0]), "=r"(vb8[1]), "=r"(vb8[2]), "=r"(vb8[3]), "=r"(vb8[4]), "=r"(vb8[5]), "=r"(vb8[6]), "=r"(vb8[7])
+                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BLOCK_N + acc * 16));
+            tmem_ld_wait();
+            if (row < M) atomicAdd(ep.bias_grad + row, __uint_as_float(vb8[0]) * ep.alpha);
+          }
           uint32_t va[32];
           if (n0 + half * 32 < N) tmem_ld_32x32(trow + half * 32, va);
 #pragma unroll 1
@@ -619,12 +646,12 @@ static int make_tmap_f32(CUtensorMap* tm, const void* ptr, uint64_t inner, uint6
   return 0;
 }
 
-template <int BN, bool AK, bool BK, int MODE>
+template <int BN, bool AK, bool BK, int MODE, bool BG = false>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, void* C,
                       long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
                       const GemmEpilogue& ep, int grid, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_sm100_kernel<BN, AK, BK, MODE>;
+  using Cfg = GemmCfg<BN, BG>;
+  auto kern = gemm_sm100_kernel<BN, AK, BK, MODE, BG>;
   static bool attr_done = false;
   if (!attr_done) {
     VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -662,6 +689,17 @@ bool gemm_sm100_eligible(const void* A, const void* B, long long lda, long long 
   return true;
 }
 
+// Whether gemm_sm100 can produce the bias gradient inside the weight-gradient launch (same conditions as its TMA
+// reduce-add epilogue); otherwise the caller adds a separate column-sum launch.
+bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor) {
+#ifdef VALOR_DEBUG
+  { const char* e = getenv("VALOR_GEMM_NO_TMA_REDUCE"); if (e && atoi(e)) return false; }
+#endif
+  return ep.accumulate && ep.out_dtype == VALOR_DT_F32 && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0) &&
+         ep.bias == nullptr && ep.residual == nullptr && ep.act_aux == nullptr && ep.preact_out == nullptr &&
+         ep.act == VALOR_ACT_NONE && !a_kmajor && !b_kmajor;
+}
+
 int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor, void* C,
                long long ldc, int M, int N, int K, const GemmEpilogue& ep, int force_bn, int force_splits,
                cudaStream_t st) {
@@ -678,13 +716,14 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   } else {
     const int cands[3] = {256, 192, 128};
     long best = -1;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = (ep.bias_grad != nullptr ? 1 : 0); i < 3; ++i) {   // fused bias gradient: 2 x BLOCK_N + 32 accumulator columns
       long waste = (long)((N + cands[i] - 1) / cands[i]) * cands[i] - N;
       if (best < 0 || waste < best) { best = waste; bn = cands[i]; }
     }
     if (N <= 64) bn = 64;
     while (bn > 64 && (long)m_blocks * ((N + bn - 1) / bn) < sms && !ep.accumulate) bn = (bn == 192) ? 128 : bn / 2;
   }
+  if (ep.bias_grad != nullptr && bn > 192) bn = 192;
   const int n_blocks = (N + bn - 1) / bn;
   const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
   int k_splits = 1;
@@ -742,6 +781,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   const bool acc_tma = ep.accumulate && ep.out_dtype == VALOR_DT_F32 && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0) &&
                        ep.bias == nullptr && ep.residual == nullptr && ep.act_aux == nullptr && ep.preact_out == nullptr &&
                        ep.act == VALOR_ACT_NONE && !a_kmajor && !b_kmajor && !no_acc_tma;
+  VALOR_REQUIRE(ep.bias_grad == nullptr || acc_tma, "gemm_sm100: bias_grad rides on the TMA reduce-add weight-gradient path only");
   if (acc_tma) {
     tma_store = 1;
     if (make_tmap_f32(&tc, C, N, M, ldc)) return 1;
@@ -782,6 +822,13 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     }
   }
   if (!a_kmajor && b_kmajor) VALOR_LAUNCH(false, true, EPI_GENERIC);
+  if (mode == EPI_ACC && ep.bias_grad != nullptr) {   // weight gradient + bias gradient in one launch (BLOCK_N <= 192: TMEM)
+    switch (bn) {
+      case 64: return launch_cfg<64, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+      case 128: return launch_cfg<128, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+      default: return launch_cfg<192, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+    }
+  }
   if (mode == EPI_ACC) VALOR_LAUNCH(false, false, EPI_ACC);
   VALOR_LAUNCH(false, false, EPI_GENERIC);
 #undef VALOR_LAUNCH

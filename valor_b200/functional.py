@@ -45,9 +45,11 @@ def fused_lin(weights, biases=None):
 
 
 def _wgrad(lin, dy, x):
+    """dW += dy^T x and db += colsum(dy): one launch (the bias gradient rides the weight-gradient GEMM as a ones-column
+    MMA on the dy tiles already in shared memory)."""
     if lin.w_grad is not None:
-        K.gemm(dy, x, a_kmajor=False, b_kmajor=False, out=lin.w_grad, accumulate=True)
-    if lin.b_grad is not None:
+        K.gemm(dy, x, a_kmajor=False, b_kmajor=False, out=lin.w_grad, accumulate=True, bias_grad=lin.b_grad)
+    elif lin.b_grad is not None:
         K.colsum(dy, lin.b_grad)
 
 

@@ -52,7 +52,7 @@ def _ld(t):
 # ------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residual=None, act_aux=None,
          want_preact=False, out=None, out_dtype=None, accumulate=False, alpha=1.0, backend=BACKEND_AUTO,
-         force_bn=0, force_splits=0):
+         force_bn=0, force_splits=0, bias_grad=None):
     """C[M,N] (+)= epi(alpha * A . B^T); a: [M,K] (k-major) or [K,M]; b: [N,K] (k-major) or [K,N]."""
     M, K = (a.shape if a_kmajor else (a.shape[1], a.shape[0]))
     N, Kb = (b.shape if b_kmajor else (b.shape[1], b.shape[0]))
@@ -78,6 +78,9 @@ def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residua
     ep.out_dtype = DT(out)
     ep.accumulate = 1 if accumulate else 0
     ep.alpha = alpha
+    ep.bias_grad = bias_grad.data_ptr() if bias_grad is not None else None
+    if bias_grad is not None:
+        assert bias_grad.dtype == torch.float32 and bias_grad.numel() == M and not a_kmajor and not b_kmajor and accumulate
     _call("valor_gemm", DT(a), P(a), _ld(a), int(a_kmajor), P(b), _ld(b), int(b_kmajor), P(out), _ld(out), M, N, K,
           ctypes.byref(ep), backend, force_bn, force_splits, ST())
     return (out, preact) if want_preact else out
