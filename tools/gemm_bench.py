@@ -41,7 +41,37 @@ def bench(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+WGRAD = [  # (name, rows, out features, in features): Linear backward of the VALOR-base step
+    ("swin1.qkv", 802816, 384, 128), ("swin1.proj", 802816, 128, 128), ("swin1.fc1", 802816, 512, 128), ("swin1.fc2", 802816, 128, 512),
+    ("swin2.qkv", 200704, 768, 256), ("swin2.fc2", 200704, 256, 1024),
+    ("swin3.qkv", 50176, 1536, 512), ("swin3.proj", 50176, 512, 512), ("swin3.fc1", 50176, 2048, 512), ("swin3.fc2", 50176, 512, 2048),
+    ("swin4.fc1", 12544, 4096, 1024), ("ast.qkv", 8256, 2304, 768), ("ast.fc2", 8256, 768, 3072),
+    ("bert.qkv", 3072, 2304, 768), ("bert.proj", 3072, 768, 768), ("bert.fc1", 3072, 3072, 768), ("bert.kv", 20800, 1536, 768),
+]
+
+
+def wgrad_ab():
+    """Linear backward: weight-gradient launch + column-sum launch vs the single launch with the bias gradient fused."""
+    for name, rows, nout, nin in WGRAD:
+        dy = torch.randn(rows, nout, device="cuda", dtype=torch.bfloat16)
+        x = torch.randn(rows, nin, device="cuda", dtype=torch.bfloat16)
+        dw = torch.zeros(nout, nin, device="cuda")
+        db = torch.zeros(nout, device="cuda")
+
+        def two():
+            K.gemm(dy, x, a_kmajor=False, b_kmajor=False, out=dw, accumulate=True)
+            K.colsum(dy, db)
+
+        ms_g = bench(lambda: K.gemm(dy, x, a_kmajor=False, b_kmajor=False, out=dw, accumulate=True))
+        ms_two = bench(two)
+        ms_one = bench(lambda: K.gemm(dy, x, a_kmajor=False, b_kmajor=False, out=dw, accumulate=True, bias_grad=db))
+        print(json.dumps({"linear": name, "rows": rows, "out": nout, "in": nin, "wgrad_ms": round(ms_g, 4),
+                          "wgrad_plus_colsum_ms": round(ms_two, 4), "fused_ms": round(ms_one, 4)}), flush=True)
+
+
 def main():
+    if "--wgrad-ab" in sys.argv:
+        return wgrad_ab()
     peak = 1400.0
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):

@@ -27,7 +27,8 @@ int check_launch(const char* what) {
 bool gemm_sm100_eligible(const void* A, const void* B, long long lda, long long ldb, int M, int N, int K);
 int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor, void* C,
                long long ldc, int M, int N, int K, const GemmEpilogue& ep, int force_bn, int force_splits, cudaStream_t st);
-bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor);
+bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor, int M, int N,
+                                int force_bn);
 int gemm_simt(int dtype, const void* A, long long sam, long long sak, const void* B, long long sbn, long long sbk,
               void* C, long long ldc, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st);
 int layernorm_fwd(int, const void*, const float*, const float*, void*, float*, float*, long long, int, float, cudaStream_t);
@@ -136,7 +137,7 @@ int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void
   if (backend == VALOR_BACKEND_TENSOR)
     VALOR_REQUIRE(tensor_ok, "valor_gemm: tensor backend requested but operands are not eligible");
   const bool use_tensor = backend == VALOR_BACKEND_TENSOR || (backend == VALOR_BACKEND_AUTO && tensor_ok);
-  if (ep.bias_grad != nullptr && !(use_tensor && gemm_sm100_fuses_bias_grad(C, ldc, ep, a_kmajor, b_kmajor))) {
+  if (ep.bias_grad != nullptr && !(use_tensor && gemm_sm100_fuses_bias_grad(C, ldc, ep, a_kmajor, b_kmajor, M, N, force_bn))) {
     // not fusable here (fp32 operands / odd pitches): the bias gradient is its own column-sum launch over A = dY [K, M]
     VALOR_REQUIRE(ep.alpha == 1.f, "valor_gemm: unfused bias_grad needs alpha = 1");
     if (colsum(dtype, A, lda, ep.bias_grad, K, M, ST)) return 1;

@@ -689,9 +689,29 @@ bool gemm_sm100_eligible(const void* A, const void* B, long long lda, long long 
   return true;
 }
 
+// BLOCK_N: least padding waste, then enough tiles to fill the machine
+static int pick_block_n(int M, int N, int accumulate, int sms) {
+  const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  const int cands[3] = {256, 192, 128};
+  int bn = 256;
+  long best = -1;
+  for (int i = 0; i < 3; ++i) {
+    long waste = (long)((N + cands[i] - 1) / cands[i]) * cands[i] - N;
+    if (best < 0 || waste < best) { best = waste; bn = cands[i]; }
+  }
+  if (N <= 64) bn = 64;
+  while (bn > 64 && (long)m_blocks * ((N + bn - 1) / bn) < sms && !accumulate) bn = (bn == 192) ? 128 : bn / 2;
+  return bn;
+}
+
 // Whether gemm_sm100 can produce the bias gradient inside the weight-gradient launch (same conditions as its TMA
 // reduce-add epilogue); otherwise the caller adds a separate column-sum launch.
-bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor) {
+// The fused form holds 2 x BLOCK_N + 32 accumulator columns, so it exists for BLOCK_N <= 192 only; where the plain launch
+// would run 256-wide tiles the narrower tile costs more operand traffic than the column-sum launch it saves (measured:
+// tools/gemm_bench.py --wgrad-ab), so those shapes keep two launches unless the caller forces a tile width.
+bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor, int M, int N,
+                                int force_bn) {
+  if ((force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, num_sms())) > 192) return false;
 #ifdef VALOR_DEBUG
   { const char* e = getenv("VALOR_GEMM_NO_TMA_REDUCE"); if (e && atoi(e)) return false; }
 #endif
@@ -709,20 +729,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   VALOR_REQUIRE(ep.act_aux == nullptr || ep.aux_dtype == VALOR_DT_BF16, "gemm_sm100: act_aux must be bf16");
   const int sms = num_sms();
   const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
-  // ---- BLOCK_N: least padding waste, then enough tiles to fill the machine
-  int bn = 256;
-  if (force_bn) {
-    bn = force_bn;
-  } else {
-    const int cands[3] = {256, 192, 128};
-    long best = -1;
-    for (int i = (ep.bias_grad != nullptr ? 1 : 0); i < 3; ++i) {   // fused bias gradient: 2 x BLOCK_N + 32 accumulator columns
-      long waste = (long)((N + cands[i] - 1) / cands[i]) * cands[i] - N;
-      if (best < 0 || waste < best) { best = waste; bn = cands[i]; }
-    }
-    if (N <= 64) bn = 64;
-    while (bn > 64 && (long)m_blocks * ((N + bn - 1) / bn) < sms && !ep.accumulate) bn = (bn == 192) ? 128 : bn / 2;
-  }
+  int bn = force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, sms);
   if (ep.bias_grad != nullptr && bn > 192) bn = 192;
   const int n_blocks = (N + bn - 1) / bn;
   const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;

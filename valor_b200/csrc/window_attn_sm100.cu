@@ -67,6 +67,10 @@ __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("b
                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),           \
                  "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),         \
                  "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory")
+#define VALOR_TMEM_LD8(taddr, v)                                                                                        \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                            \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])          \
+               : "r"(taddr))
 #define VALOR_TMEM_LD16(taddr, v)                                                                                       \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"                                                                  \
                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                           \
@@ -79,6 +83,15 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *(uint32_t*)&v; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of arithmetic)
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// read-only table lookup: not volatile, so independent lookups can be hoisted and issued together
+__device__ __forceinline__ float lds_ro_f32(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_ro_v4(uint32_t a) { uint4 v; asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int nbytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
@@ -482,14 +495,18 @@ window_fwd_sm100_kernel(FwdParams P) {
 //   [128,256) dP  = dO_qt . V_kt^T
 //   [256,384) dQ_qt accumulators (4 x 32 columns), live across the k-tiles
 //   [384,512) dK | dV accumulators of the current k-tile, double-buffered (2 x (32 + 32))
-// Sixteen element warps (tensor-memory lane quarter x 32-key column group), one query row per thread:
-// p = exp2(s*scale2 + bias2 - lse2), ds = p * (dP - delta); bf16 P and dS go ONCE into 128-byte-swizzled [query][key]
-// panels that serve  dV += P^T.dO  and  dK += dS^T.Q  as MN-major A operands and  dQ += dS.K  as a K-major A operand.
-// Bias-table gradient: fp32 ds is folded into the warp's private slice (plain load / add / store: inside one key
-// column the 32 queries of a warp hit distinct slots and a warp's shared-memory instructions retire in order); a
-// slice only spans (32 queries + 32 keys) of relative-position codes, is double-buffered, and is merged into the CTA
-// table by all element threads while the next block is already being processed; the CTA table goes to global memory
-// once per (window, head).
+// Sixteen element warps (tensor-memory lane quarter x 32-key column group), one query row per thread, four batches of
+// 8 key columns per block: p = exp2(s*scale2 + bias2 - lse2), ds = p * (dP - delta) on packed fp32 pairs; bf16 P and dS
+// go ONCE into 128-byte-swizzled [query][key] panels that serve  dV += P^T.dO  and  dK += dS^T.Q  as MN-major A operands
+// and  dQ += dS.K  as a K-major A operand.
+// Bias-table gradient: fp32 ds is folded into the warp's private slice (plain load / add / store in column order: inside
+// one key column the 32 queries of a warp hit distinct slots and a warp's shared-memory instructions retire in order); a
+// slice only spans (32 queries + 32 keys) of relative-position codes and is double-buffered.  Warps 2 and 3 merge the
+// slices of block b into their own copy of the CTA table while the element warps work on block b + 1 (mbarrier
+// hand-off both ways, no CTA-wide barrier in the main loop) and write the table out once per (window, head).  Warp 2
+// also reloads the K / V tile between k-tiles; warp 3 prefetches that tile's rows into L2 one k-tile ahead.
+// Measured anatomy of one block (tools/probe/run_trace.py): the element warps are never waiting for the tensor core;
+// they are bound by their own instruction issue and the ordered fold chain.
 struct BwdParams {
   const bf16* qkv; long long ld;
   const bf16* O; const bf16* dO; long long ldo;
@@ -512,7 +529,7 @@ struct BwdSmem {
   int* qrow; uint32_t *qcode, *kcode, *qreg;
   float* tab2;
   float* ld2;           // [512][2]: lse * log2e (+inf on padding rows), -delta
-  float* ctab;          // CTA-level bias-table gradient [n_used]
+  float* ctab;          // CTA-level bias-table gradient, one copy per merge warp: [2][n_used rounded to 16 bytes]
   unsigned char* gpriv; // [2 buffers][16 warps][gt_bytes]
   int* winfo;           // [2 buffers][8]: qlo[4] (first query code word of each lane quarter), khi[4] (last key code word of each column group)
   uint64_t* bars;
@@ -528,7 +545,7 @@ static inline size_t bwd_smem_bytes(int nqt, int n_used, int gt_bytes, bool want
   const size_t tabb = ((size_t)n_used * 4 + 15) / 16 * 16;
   b += tabb;
   b += 512 * 2 * 4;
-  if (want_dtab) b += tabb + (size_t)2 * NEW * gt_bytes;
+  if (want_dtab) b += 2 * tabb + (size_t)2 * NEW * gt_bytes;   // two CTA tables (one per merge warp) + private slices
   b += 2 * 8 * 4;
   b += 16 * 8 + 16;
   return b;
@@ -553,7 +570,7 @@ __device__ __forceinline__ BwdSmem bwd_carve(unsigned char* raw, const BwdParams
   S.ld2 = (float*)((unsigned char*)S.tab2 + tabb);
   unsigned char* nxt = (unsigned char*)(S.ld2 + 1024);
   S.ctab = (float*)nxt;
-  S.gpriv = nxt + tabb;
+  S.gpriv = nxt + 2 * tabb;
   if (P.dtable != nullptr) nxt = S.gpriv + (size_t)2 * NEW * P.gt_bytes;
   S.winfo = (int*)nxt;
   S.bars = (uint64_t*)(S.winfo + 16);
@@ -562,50 +579,69 @@ __device__ __forceinline__ BwdSmem bwd_carve(unsigned char* raw, const BwdParams
 }
 
 constexpr int TB_S = 0, TB_DP = 128, TB_DQ = 256, TB_DKV = 384;
+#if defined(VALOR_EXP) && (VALOR_EXP & 8)
+// (experiment build only) cycle stamps of one CTA: g_trace[block][slot]
+__device__ long long g_trace[64 * 32];
+#define VALOR_TRACE(b, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_trace[(b) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define VALOR_TRACE(b, slot) do { } while (0)
+#endif
 __device__ __forceinline__ float ldv_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void stv_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
 
 // barrier slots
-enum { B_SFULL = 0, B_SFREE = 2, B_PDFULL = 4, B_PDFREE = 5, B_KVFULL = 6, B_KVLOAD = 8, B_QFULL = 9 };
+enum { B_SFULL = 0, B_SFREE = 2, B_PDFULL = 4, B_PDFREE = 5, B_KVFULL = 6, B_KVLOAD = 8, B_QFULL = 9, B_FOLDFULL = 10, B_FLDONE = 12 };
 
-// 16 key columns of one query row: probabilities, dS, bias-gradient fold, bf16 packing.  TAIL: only the first `nv`
-// columns hold real keys (the others produce zeros and are not folded).
+// 8 key columns of one query row: probabilities, dS, bias-gradient fold, bf16 packing (one 16-byte panel chunk each).
+// TAIL: only the first `nv` columns hold real keys (the others produce zeros and are not folded).
+// The work is staged so that independent instructions sit next to each other (the element warps are issue-latency
+// bound, four warps per scheduler): all bias lookups, then the exponentials, then the ordered fold.
 template <bool MASKED, bool TAIL>
-__device__ __forceinline__ void bwd_cols16(const uint32_t* sv, const uint32_t* dv, uint32_t kc_s, uint32_t kr_s, int kg, int nv,
-                                           uint32_t qaddr, uint32_t gaddr, uint32_t qrg, float scale2, float l2, float nd,
-                                           bool want_dtab, uint32_t* pw, uint32_t* dw) {
+__device__ __forceinline__ void bwd_cols8(const uint32_t* sv, const uint32_t* dv, uint32_t kc_s, uint32_t kr_s, int kg, int nv,
+                                          uint32_t qaddr, uint32_t gaddr, uint32_t qrg, float scale2, float l2, float nd,
+                                          bool want_dtab, uint4& pw, uint4& dw) {
   const float kMask2 = -100.0f * kLog2e;
-  uint32_t kc[16], kr[16];
+  uint32_t kc[8], kr[8];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint4 t = lds_v4(kc_s + (kg + g * 4) * 4);
+  for (int g = 0; g < 2; ++g) {
+    const uint4 t = lds_ro_v4(kc_s + (kg + g * 4) * 4);
     kc[g * 4] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
     if (MASKED) {
-      const uint4 u = lds_v4(kr_s + (kg + g * 4) * 4);
+      const uint4 u = lds_ro_v4(kr_s + (kg + g * 4) * 4);
       kr[g * 4] = u.x; kr[g * 4 + 1] = u.y; kr[g * 4 + 2] = u.z; kr[g * 4 + 3] = u.w;
     }
   }
-  float pf[16], df[16];
+  float pf[8], df[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float x = fmaf(__uint_as_float(sv[j]), scale2, lds_f32(qaddr - kc[j]));
-    if (MASKED && qrg != kr[j]) x += kMask2;
-    float pr = ex2f(x - l2);                   // l2 = +inf on padding queries -> 0
-    if (TAIL && j >= nv) pr = 0.f;             // padding key (warp-uniform)
-    pf[j] = pr;
-    df[j] = pr * (__uint_as_float(dv[j]) + nd);
+  for (int j = 0; j < 8; ++j) pf[j] = lds_ro_f32(qaddr - kc[j]);        // stage 1: bias lookups (read-only table)
+  // stage 2: probabilities and ds, two columns per instruction (packed fp32 pairs: the element warps are issue bound)
+  const uint64_t sc2 = pk2(scale2, scale2), nl2 = pk2(-l2, -l2), nd2 = pk2(nd, nd);
+#pragma unroll
+  for (int jp = 0; jp < 4; ++jp) {
+    const int j = 2 * jp;
+    float x0, x1;
+    upk2(fadd2(ffma2(pk2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, pk2(pf[j], pf[j + 1])), nl2), x0, x1);
+    if (MASKED && qrg != kr[j]) x0 += kMask2;
+    if (MASKED && qrg != kr[j + 1]) x1 += kMask2;
+    float p0 = ex2f(x0), p1 = ex2f(x1);          // l2 = +inf on padding queries -> 0
+    if (TAIL && j >= nv) p0 = 0.f;               // padding keys (warp-uniform)
+    if (TAIL && j + 1 >= nv) p1 = 0.f;
+    pf[j] = p0; pf[j + 1] = p1;
+    upk2(fmul2(pk2(p0, p1), fadd2(pk2(__uint_as_float(dv[j]), __uint_as_float(dv[j + 1])), nd2)), df[j], df[j + 1]);
   }
+  // stage 3: bias-gradient fold, strictly in column order (lanes of neighbouring queries meet the same slot one column
+  // apart: the load / add / store triples must not be interleaved across columns)
   if (want_dtab) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
       if (!TAIL || j < nv) {
         const uint32_t slot = gaddr - kc[j];
         stv_f32(slot, ldv_f32(slot) + df[j]);
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]); dw[j] = pack_bf16(df[2 * j], df[2 * j + 1]); }
+  pw.x = pack_bf16(pf[0], pf[1]); pw.y = pack_bf16(pf[2], pf[3]); pw.z = pack_bf16(pf[4], pf[5]); pw.w = pack_bf16(pf[6], pf[7]);
+  dw.x = pack_bf16(df[0], df[1]); dw.y = pack_bf16(df[2], df[3]); dw.z = pack_bf16(df[4], df[5]); dw.w = pack_bf16(df[6], df[7]);
 }
 
 template <bool MASKED>
@@ -624,34 +660,6 @@ __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdS
   const uint32_t pb_s = s_u32(S.Pb) + half * 16384 + rloc * 128, dsb_s = s_u32(S.dSb) + half * 16384 + rloc * 128;
   const int sw = rloc & 7;
   const int cbase = (grp & 1) * 4;                        // first 16-byte chunk of this group inside the 64-key panel row
-  // merge of a block's private slices into the CTA table (runs while the MMAs of that block are in flight)
-  auto flush = [&](int b) {
-    const int kt = b / P.nqt, qt = b % P.nqt;
-    const int* wi = S.winfo + (b & 1) * 8;
-    int qlo[4], khi[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { qlo[i] = wi[i]; khi[i] = wi[4 + i]; }
-    const int ulo = (int)S.qcode[qt * 128] - (int)S.kcode[min(kt * 128 + 127, N - 1)];
-    const int uhi = (int)S.qcode[min(qt * 128 + 127, N - 1)] - (int)S.kcode[kt * 128];
-    const uint32_t gp = s_u32(S.gpriv) + (uint32_t)((b & 1) * NEW * P.gt_bytes);
-    for (int sb = ulo + 4 * et; sb <= uhi; sb += 4 * NET) {
-      float acc = 0.f;
-#pragma unroll
-      for (int qi = 0; qi < 4; ++qi) {
-        const int d = sb - qlo[qi];
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const uint32_t off = (uint32_t)(d + khi[gi]);      // negative -> huge -> fails the unsigned range test
-          if (off < (uint32_t)P.gt_bytes) {
-            const uint32_t a = gp + (uint32_t)((gi * 4 + qi) * P.gt_bytes) + off;
-            acc += ldv_f32(a);
-            stv_f32(a, 0.f);
-          }
-        }
-      }
-      S.ctab[sb >> 2] += acc;
-    }
-  };
   for (int kt = 0; kt < P.nkt; ++kt) {
     const int k0 = kt * 128 + grp * 32;                   // first key of this warp's column group
     const int nvk = min(32, N - k0);                      // real keys in the group (<= 0: none)
@@ -663,57 +671,71 @@ __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdS
       const bool live = nvk > 0 && q0 < N;
       const uint32_t qcode = S.qcode[min(q, N - 1)];        // padding lanes fold zeros into a valid slot
       const int qc0 = (int)S.qcode[min(q0, N - 1)];
-      const int lo_b = qc0 - kc_hi;                        // smallest slot byte offset this warp touches in this block
+      const int lo_b = (qc0 - kc_hi) & ~15;                // 16-byte aligned origin of the slot range this warp touches in this block
       const uint32_t qaddr = tab_s + qcode;
       const uint32_t gaddr = s_u32(S.gpriv) + (uint32_t)(((b & 1) * NEW + e) * P.gt_bytes) + qcode - (uint32_t)lo_b;
       const uint32_t qrg = S.qreg[min(q, N - 1)];
       const float l2 = S.ld2[2 * q], nd = S.ld2[2 * q + 1];
+      if (want_dtab && b >= 2) bar_wait(&bars[B_FLDONE + (b & 1)], ((b >> 1) - 1) & 1);   // block b-2's slices are merged and zeroed
       if (want_dtab && lane == 0) {                       // this block's slice origins (same value from every warp of a row / column)
         if (grp == 0) S.winfo[(b & 1) * 8 + qtr] = q0 < N ? qc0 : (1 << 28);
         if (qtr == 0) S.winfo[(b & 1) * 8 + 4 + grp] = nvk > 0 ? kc_hi : -(1 << 28);
       }
+      if (lane == 0 && qtr == 0 && (grp & 1) == 0) VALOR_TRACE(b, 0 + half * 8);
       bar_wait(&bars[B_SFULL + half], b & 1);
       tc_fence_after();
-      uint32_t pw[2][8], dw[2][8];
+      if (lane == 0 && qtr == 0 && (grp & 1) == 0) VALOR_TRACE(b, 1 + half * 8);
+      // four batches of 8 key columns; each batch leaves as one 16-byte chunk of the P and dS panel rows
+      uint4 pw0 = make_uint4(0u, 0u, 0u, 0u), dw0 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = grp * 32 + sub * 16;               // column inside the 128-key block
-        const int nv = nvk - sub * 16;                    // real keys among these 16 columns
+      for (int bt = 0; bt < 4; ++bt) {
+        const int c0 = grp * 32 + bt * 8;                 // column inside the 128-key block
+        const int nv = nvk - bt * 8;                      // real keys among these 8 columns
 #if defined(VALOR_EXP) && (VALOR_EXP & 2)
-        if (false) {
+        const bool act = false;
 #else
-        if (live && nv > 0) {
+        const bool act = live && nv > 0;
 #endif
-          uint32_t sv[16], dv[16];
-          VALOR_TMEM_LD16(lane_t + TB_S + c0, sv);
-          VALOR_TMEM_LD16(lane_t + TB_DP + c0, dv);
+        uint32_t sv[8], dv[8];
+        if (act) {
+          VALOR_TMEM_LD8(lane_t + TB_S + c0, sv);
+          VALOR_TMEM_LD8(lane_t + TB_DP + c0, dv);
           tmem_wait_ld();
-          if (nv >= 16) bwd_cols16<MASKED, false>(sv, dv, kc_s, kr_s, kt * 128 + c0, 16, qaddr, gaddr, qrg, P.scale2, l2, nd, want_dtab, pw[sub], dw[sub]);
-          else bwd_cols16<MASKED, true>(sv, dv, kc_s, kr_s, kt * 128 + c0, nv, qaddr, gaddr, qrg, P.scale2, l2, nd, want_dtab, pw[sub], dw[sub]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pw[sub][j] = dw[sub][j] = 0u;
         }
-      }
-      tc_fence_before();                                  // every tensor-memory read of this block is in registers
-      __syncwarp();
-      if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
-      if (b > 0) bar_wait(&bars[B_PDFREE], (b - 1) & 1);  // the previous block's dV / dK / dQ MMAs have read the panels
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const uint32_t o0 = (uint32_t)(((cbase + sub * 2) ^ sw) << 4), o1 = (uint32_t)(((cbase + sub * 2 + 1) ^ sw) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o0), "r"(pw[sub][0]), "r"(pw[sub][1]), "r"(pw[sub][2]), "r"(pw[sub][3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o1), "r"(pw[sub][4]), "r"(pw[sub][5]), "r"(pw[sub][6]), "r"(pw[sub][7]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o0), "r"(dw[sub][0]), "r"(dw[sub][1]), "r"(dw[sub][2]), "r"(dw[sub][3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o1), "r"(dw[sub][4]), "r"(dw[sub][5]), "r"(dw[sub][6]), "r"(dw[sub][7]) : "memory");
+        if (lane == 0 && e == 0) VALOR_TRACE(b, 20 + (bt >> 1) * 2);
+        if (bt == 3) {                                    // every tensor-memory read of this block is in registers:
+          tc_fence_before();                              // the next block's S / dP MMAs overlap the rest of this one
+          __syncwarp();
+          if (lane == 0) bar_arrive(&bars[B_SFREE + half]);
+        }
+        uint4 pw = make_uint4(0u, 0u, 0u, 0u), dw = make_uint4(0u, 0u, 0u, 0u);
+        if (act) {
+          if (nv >= 8) bwd_cols8<MASKED, false>(sv, dv, kc_s, kr_s, kt * 128 + c0, 8, qaddr, gaddr, qrg, P.scale2, l2, nd, want_dtab, pw, dw);
+          else bwd_cols8<MASKED, true>(sv, dv, kc_s, kr_s, kt * 128 + c0, nv, qaddr, gaddr, qrg, P.scale2, l2, nd, want_dtab, pw, dw);
+        }
+        if (lane == 0 && e == 0) VALOR_TRACE(b, 21 + (bt >> 1) * 2);
+        // the panels still belong to the previous block's dV / dK / dQ MMAs for a while: the first two batches are
+        // held in registers and stored together, which hides that wait behind the second batch's arithmetic
+        if (bt == 0) { pw0 = pw; dw0 = dw; continue; }
+        if (bt == 1) {
+          if (lane == 0 && qtr == 0 && (grp & 1) == 0) VALOR_TRACE(b, 2 + half * 8);
+          if (b > 0) bar_wait(&bars[B_PDFREE], (b - 1) & 1);
+          if (lane == 0 && qtr == 0 && (grp & 1) == 0) VALOR_TRACE(b, 3 + half * 8);
+          const uint32_t o0 = (uint32_t)((cbase ^ sw) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o0), "r"(pw0.x), "r"(pw0.y), "r"(pw0.z), "r"(pw0.w) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o0), "r"(dw0.x), "r"(dw0.y), "r"(dw0.z), "r"(dw0.w) : "memory");
+        }
+        const uint32_t o = (uint32_t)(((cbase + bt) ^ sw) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pb_s + o), "r"(pw.x), "r"(pw.y), "r"(pw.z), "r"(pw.w) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dsb_s + o), "r"(dw.x), "r"(dw.y), "r"(dw.z), "r"(dw.w) : "memory");
       }
       proxy_fence();
       __syncwarp();
-      if (lane == 0) bar_arrive(&bars[B_PDFULL]);
-      if (want_dtab) {
-        named_bar(5, NET);                                // every element warp has finished this block's folds
-        flush(b);
+      if (lane == 0) {
+        bar_arrive(&bars[B_PDFULL]);
+        if (want_dtab) bar_arrive(&bars[B_FOLDFULL + (b & 1)]);   // this warp's folds of block b are in its private slice
       }
+      if (lane == 0 && qtr == 0 && (grp & 1) == 0) VALOR_TRACE(b, 4 + half * 8);
     }
     // ---------------- k-tile epilogue: dK (column groups 0,1) / dV (groups 2,3) rows of this tile, 16 channels per warp
     bar_wait(&bars[B_KVFULL + (kt & 1)], (kt >> 1) & 1);
@@ -764,12 +786,48 @@ __device__ __forceinline__ void bwd_element_warps(const BwdParams& P, const BwdS
     }
   }
   tc_fence_before();
-  if (want_dtab) {
-    named_bar(5, NET);                                    // the last block's merge is complete
-    const int r0 = P.center - P.maxcode;
-    for (int r = et; r < P.n_used; r += NET) {
-      const float v = S.ctab[r];
-      if (v != 0.f) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], v);
+}
+
+// Warps 2 and 3: merge the element warps' private bias-gradient slices into a CTA table one block behind them (the
+// slices are double-buffered).  Each merge warp owns eight slices and its own copy of the CTA table, so the two never
+// touch the same word; a slice and the table range it maps to are both 16-byte aligned: 128-bit loads / stores, three
+// independent chunks in flight per lane.
+__device__ __forceinline__ uint4 ldv_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void stv_v4(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void bwd_merge_block(const BwdParams& P, const BwdSmem& S, int b, int fw, int lane) {
+  const int* wi = S.winfo + (b & 1) * 8;
+  const uint32_t gp = s_u32(S.gpriv) + (uint32_t)((b & 1) * NEW * P.gt_bytes);
+  const uint32_t ct = s_u32(S.ctab) + (uint32_t)fw * (uint32_t)(((size_t)P.n_used * 4 + 15) / 16 * 16);
+  const int nch = P.gt_bytes >> 4;
+#pragma unroll 1
+  for (int s = fw; s < NEW; s += 2) {
+    const int qlo = wi[s & 3], khi = wi[4 + (s >> 2)];
+    if (qlo >= (1 << 28) || khi <= -(1 << 28)) continue;    // that warp had no live rows / keys in this block
+    const uint32_t o = (uint32_t)((qlo - khi) & ~15);       // byte offset of the slice's first slot inside the table
+    const uint32_t sl = gp + (uint32_t)(s * P.gt_bytes);
+#pragma unroll 1
+    for (int c0 = 0; c0 < nch; c0 += 96) {
+      uint4 v[3];
+      bool nz[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int c = c0 + u * 32 + lane;
+        v[u] = c < nch ? ldv_v4(sl + 16 * c) : make_uint4(0u, 0u, 0u, 0u);
+        nz[u] = ((v[u].x | v[u].y | v[u].z | v[u].w) << 1) != 0u;      // anything but +-0
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int c = c0 + u * 32 + lane;
+        if (nz[u]) {
+          stv_v4(sl + 16 * c, make_uint4(0u, 0u, 0u, 0u));
+          uint4 t = ldv_v4(ct + o + 16 * c);
+          t.x = __float_as_uint(__uint_as_float(t.x) + __uint_as_float(v[u].x));
+          t.y = __float_as_uint(__uint_as_float(t.y) + __uint_as_float(v[u].y));
+          t.z = __float_as_uint(__uint_as_float(t.z) + __uint_as_float(v[u].z));
+          t.w = __float_as_uint(__uint_as_float(t.w) + __uint_as_float(v[u].w));
+          stv_v4(ct + o + 16 * c, t);
+        }
+      }
     }
   }
 }
@@ -788,7 +846,9 @@ window_bwd_sm100_kernel(BwdParams P) {
     bar_init(&bars[B_SFREE], NEW / 2); bar_init(&bars[B_SFREE + 1], NEW / 2);
     bar_init(&bars[B_PDFULL], NEW); bar_init(&bars[B_PDFREE], 1);
     bar_init(&bars[B_KVFULL], 1); bar_init(&bars[B_KVFULL + 1], 1);
-    bar_init(&bars[B_KVLOAD], 64); bar_init(&bars[B_QFULL], 1);
+    bar_init(&bars[B_KVLOAD], 32); bar_init(&bars[B_QFULL], 1);
+    bar_init(&bars[B_FOLDFULL], NEW); bar_init(&bars[B_FOLDFULL + 1], NEW);
+    bar_init(&bars[B_FLDONE], 2); bar_init(&bars[B_FLDONE + 1], 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -798,7 +858,7 @@ window_bwd_sm100_kernel(BwdParams P) {
   const bool masked = build_tables(P.win, P.maxcode, P.center, P.n_used, p, h, S.qrow, S.qcode, S.kcode, S.qreg, S.tab2, 512);
   if (P.dtable != nullptr) {
     float* z = S.ctab;
-    const int nz = (int)(((size_t)P.n_used * 4 + 15) / 16 * 4) + 2 * NEW * P.gt_bytes / 4;   // CTA table + private slices (contiguous)
+    const int nz = 2 * (int)(((size_t)P.n_used * 4 + 15) / 16 * 4) + 2 * NEW * P.gt_bytes / 4;   // CTA tables + private slices (contiguous)
     for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0.f;
   }
   __syncthreads();
@@ -808,18 +868,27 @@ window_bwd_sm100_kernel(BwdParams P) {
   gather_rows(S.Vs, P.qkv + 2 * C, P.ld, col0, S.qrow, 128);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = threadIdx.x; i < 512; i += blockDim.x) S.ld2[2 * i] = i < N ? P.lse[((size_t)p * P.heads + h) * N + i] * kLog2e : INFINITY;
+  // -delta_i = -(dO_i . O_i): dO from the staged tile, O rows straight from global memory (four lanes per row); the O
+  // loads are issued before the wait on the staged tiles so both memory round trips overlap
+  constexpr int kDeltaIters = (512 * 4 + 128 + NET - 1) / (128 + NET);
+  uint4 o4[kDeltaIters];
+#pragma unroll
+  for (int it = 0; it < kDeltaIters; ++it) {
+    const int c = threadIdx.x + it * (128 + NET);
+    const int gr = c < 512 * 4 ? S.qrow[c >> 2] : -1;
+    o4[it] = gr >= 0 ? *(const uint4*)(P.O + (size_t)gr * P.ldo + col0 + (c & 3) * 8) : make_uint4(0u, 0u, 0u, 0u);
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // -delta_i = -(dO_i . O_i): dO from the staged tile, O rows straight from global memory; four lanes per row
-  for (int c = threadIdx.x; c < 512 * 4; c += blockDim.x) {
+#pragma unroll
+  for (int it = 0; it < kDeltaIters; ++it) {
+    const int c = threadIdx.x + it * (128 + NET);
     const int r = c >> 2, ch = c & 3;
-    const int gr = S.qrow[r];
     float d = 0.f;
-    if (gr >= 0) {
-      const uint4 o4 = *(const uint4*)(P.O + (size_t)gr * P.ldo + col0 + ch * 8);
+    if (c < 512 * 4 && S.qrow[r] >= 0) {
       const uint4 a = *(const uint4*)(S.dOs + tile64(r, ch));
       const __nv_bfloat162* pa = (const __nv_bfloat162*)&a;
-      const __nv_bfloat162* po = (const __nv_bfloat162*)&o4;
+      const __nv_bfloat162* po = (const __nv_bfloat162*)&o4[it];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 fa = __bfloat1622float2(pa[j]), fo = __bfloat1622float2(po[j]);
@@ -828,7 +897,7 @@ window_bwd_sm100_kernel(BwdParams P) {
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
-    if (ch == 0) S.ld2[2 * r + 1] = -d;
+    if (c < 512 * 4 && ch == 0) S.ld2[2 * r + 1] = -d;
   }
   proxy_fence();
   tc_fence_before();
@@ -845,17 +914,24 @@ window_bwd_sm100_kernel(BwdParams P) {
       // ===================== MMA issuer =====================
       const uint32_t Qs = s_u32(S.Qs), dOs = s_u32(S.dOs), Ks = s_u32(S.Ks), Vs = s_u32(S.Vs), Pb = s_u32(S.Pb), dSb = s_u32(S.dSb);
       const uint32_t id_s = make_idesc(64, 0, 0), id_kv = make_idesc(HD, 1, 1), id_q = make_idesc(HD, 0, 1);
+      // descriptors: constant high words, low word = (address >> 4) | (LBO >> 4) << 16 advanced by plain 32-bit adds
+      // (this thread shares its scheduler with four element warps: every instruction it does not issue is MMA latency)
+      constexpr uint32_t HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29), HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+      auto lo = [](uint32_t addr, uint32_t lbo) { return ((addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); };
+      auto mk = [](uint32_t l, uint32_t h) { return ((uint64_t)h << 32) | l; };
+      const uint32_t lQ = lo(Qs, VALOR_SW64_K_LBO), lO = lo(dOs, VALOR_SW64_K_LBO), lK = lo(Ks, VALOR_SW64_K_LBO), lV = lo(Vs, VALOR_SW64_K_LBO);
+      const uint32_t lQm = lo(Qs, VALOR_SW64_MN_LBO), lOm = lo(dOs, VALOR_SW64_MN_LBO), lKm = lo(Ks, VALOR_SW64_MN_LBO);
+      const uint32_t lPm = lo(Pb, 16384), lSm = lo(dSb, 16384), lSk = lo(dSb, 0);
       auto issue_s = [&](int b) {
-        const int qt = b % P.nqt;
+        const uint32_t qoff = (uint32_t)((b % P.nqt) * 128 * ROWB) >> 4;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           if (b > 0) { bar_wait(&bars[B_SFREE + hf], (b - 1) & 1); tc_fence_after(); }
+          const uint32_t koff = (uint32_t)(hf * 64 * ROWB) >> 4;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            tc_mma(tmem + TB_S + hf * 64, smem_desc(Qs + qt * 128 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4),
-                   smem_desc(Ks + hf * 64 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4), id_s, k);
-            tc_mma(tmem + TB_DP + hf * 64, smem_desc(dOs + qt * 128 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4),
-                   smem_desc(Vs + hf * 64 * ROWB + k * 32, VALOR_SW64_K_LBO, 512, 4), id_s, k);
+            tc_mma(tmem + TB_S + hf * 64, mk(lQ + qoff + 2 * k, HI_SW64), mk(lK + koff + 2 * k, HI_SW64), id_s, k);
+            tc_mma(tmem + TB_DP + hf * 64, mk(lO + qoff + 2 * k, HI_SW64), mk(lV + koff + 2 * k, HI_SW64), id_s, k);
           }
           tc_commit(&bars[B_SFULL + hf]);
         }
@@ -865,29 +941,45 @@ window_bwd_sm100_kernel(BwdParams P) {
         const int kt = b / P.nqt, qt = b % P.nqt;
         const bool more = b + 1 < nb;
         const bool same_tile = more && (b + 1) / P.nqt == kt;
+        VALOR_TRACE(b, 16);
         if (same_tile) issue_s(b + 1);
+        VALOR_TRACE(b, 17);
         bar_wait(&bars[B_PDFULL], b & 1);
         tc_fence_after();
+        VALOR_TRACE(b, 18);
         const int kq = (min(128, N - qt * 128) + 15) / 16;       // 16-query k-steps that hold real rows
         const int kk = (min(128, N - kt * 128) + 15) / 16;       // 16-key k-steps that hold real keys
         const uint32_t tkv = tmem + TB_DKV + (kt & 1) * 64;
 #if defined(VALOR_EXP) && (VALOR_EXP & 1)
         if (false)
 #endif
-        for (int ks = 0; ks < kq; ++ks) {
-          const uint64_t bq = smem_desc(Qs + (qt * 128 + ks * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4);
-          const uint64_t bo = smem_desc(dOs + (qt * 128 + ks * 16) * ROWB, VALOR_SW64_MN_LBO, 512, 4);
-          const uint32_t acc = (qt | ks) ? 1u : 0u;
-          tc_mma(tkv, smem_desc(dSb + ks * 2048, 16384, 1024, 2), bq, id_kv, acc);        // dK += dS^T . Q
-          tc_mma(tkv + 32, smem_desc(Pb + ks * 2048, 16384, 1024, 2), bo, id_kv, acc);    // dV += P^T . dO
+        {
+          uint32_t aK = lSm, aV = lPm, bQ = lQm + ((uint32_t)(qt * 128 * ROWB) >> 4), bO = lOm + ((uint32_t)(qt * 128 * ROWB) >> 4);
+          uint32_t acc = qt ? 1u : 0u;
+#pragma unroll 1
+          for (int ks = 0; ks < kq; ++ks) {
+            tc_mma(tkv, mk(aK, HI_SW128), mk(bQ, HI_SW64), id_kv, acc);          // dK += dS^T . Q
+            tc_mma(tkv + 32, mk(aV, HI_SW128), mk(bO, HI_SW64), id_kv, acc);     // dV += P^T . dO
+            aK += 2048 >> 4; aV += 2048 >> 4; bQ += (16 * ROWB) >> 4; bO += (16 * ROWB) >> 4;
+            acc = 1u;
+          }
         }
 #if defined(VALOR_EXP) && (VALOR_EXP & 1)
         if (false)
 #endif
-        for (int ks = 0; ks < kk; ++ks)                                                   // dQ += dS . K
-          tc_mma(tmem + TB_DQ + qt * 32, smem_desc(dSb + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024, 2),
-                 smem_desc(Ks + ks * 16 * ROWB, VALOR_SW64_MN_LBO, 512, 4), id_q, (kt | ks) ? 1u : 0u);
+        {
+          uint32_t aS = lSk, bK = lKm, acc = kt ? 1u : 0u;
+          const uint32_t tq = tmem + TB_DQ + qt * 32;
+#pragma unroll 1
+          for (int ks = 0; ks < kk; ++ks) {                                        // dQ += dS . K
+            tc_mma(tq, mk(aS, HI_SW128), mk(bK, HI_SW64), id_q, acc);
+            aS += (ks == 3) ? ((16384 - 96) >> 4) : (32 >> 4);
+            bK += (16 * ROWB) >> 4;
+            acc = 1u;
+          }
+        }
         tc_commit(&bars[B_PDFREE]);
+        VALOR_TRACE(b, 19);
         if (qt == P.nqt - 1) tc_commit(&bars[B_KVFULL + (kt & 1)]);
         if (more && !same_tile) {
           bar_wait(&bars[B_KVLOAD], kt & 1);      // next K / V tile has landed
@@ -898,22 +990,51 @@ window_bwd_sm100_kernel(BwdParams P) {
       tc_commit(&bars[B_QFULL]);
     }
   } else if (warp == 2 || warp == 3) {
-    // ===================== K / V tile loader (64 threads) =====================
-    const int lt = threadIdx.x - 64;
-    for (int kt = 1; kt < P.nkt; ++kt) {
-      bar_wait(&bars[B_KVFULL + ((kt - 1) & 1)], ((kt - 1) >> 1) & 1);   // every MMA that reads the previous tile has retired
-      const uint32_t k0 = s_u32(S.Ks), v0 = s_u32(S.Vs);
-      for (int c = lt; c < 128 * 4; c += 64) {
-        const int r = c >> 2, ch = c & 3;
-        const int gr = S.qrow[kt * 128 + r];
-        const bf16* src = P.qkv + (size_t)(gr < 0 ? 0 : gr) * P.ld + col0 + ch * 8;
-        cp_async16(k0 + tile64(r, ch), src + C, gr < 0 ? 0 : 16);
-        cp_async16(v0 + tile64(r, ch), src + 2 * C, gr < 0 ? 0 : 16);
+    // ===================== K / V tile loader (warp 2) + bias-gradient merge (warps 2, 3) =====================
+    const int fw = warp - 2;
+    const bool want_dtab = P.dtable != nullptr;
+    for (int b = 0; b < nb; ++b) {
+      const int kt = b / P.nqt;
+      if (fw == 1 && b % P.nqt == 0 && kt + 1 < P.nkt) {   // next tile's K / V rows towards L2 a whole k-tile ahead of their load
+        for (int r = lane; r < 128; r += 32) {
+          const int gr = S.qrow[(kt + 1) * 128 + r];
+          if (gr >= 0) {
+            const bf16* src = P.qkv + (size_t)gr * P.ld + col0;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + C));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * C));
+          }
+        }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      proxy_fence();
-      bar_arrive(&bars[B_KVLOAD]);
+      if (fw == 0 && b % P.nqt == P.nqt - 1 && kt + 1 < P.nkt) {
+        // last block of a k-tile: the next K / V tile goes first (the S / dP MMAs of the next block wait for it)
+        bar_wait(&bars[B_KVFULL + (kt & 1)], (kt >> 1) & 1);   // every MMA that reads the current tile has retired
+        const uint32_t k0 = s_u32(S.Ks), v0 = s_u32(S.Vs);
+        for (int c = lane; c < 128 * 4; c += 32) {
+          const int r = c >> 2, ch = c & 3;
+          const int gr = S.qrow[(kt + 1) * 128 + r];
+          const bf16* src = P.qkv + (size_t)(gr < 0 ? 0 : gr) * P.ld + col0 + ch * 8;
+          cp_async16(k0 + tile64(r, ch), src + C, gr < 0 ? 0 : 16);
+          cp_async16(v0 + tile64(r, ch), src + 2 * C, gr < 0 ? 0 : 16);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        proxy_fence();
+        bar_arrive(&bars[B_KVLOAD]);
+      }
+      if (want_dtab) {
+        bar_wait(&bars[B_FOLDFULL + (b & 1)], (b >> 1) & 1);
+        bwd_merge_block(P, S, b, fw, lane);
+        __syncwarp();
+        if (lane == 0) bar_arrive(&bars[B_FLDONE + (b & 1)]);
+      }
+    }
+    if (want_dtab) {   // this warp's copy of the CTA table -> global bias-table gradient
+      const int r0 = P.center - P.maxcode;
+      const float* mine = S.ctab + (size_t)fw * (((size_t)P.n_used * 4 + 15) / 16 * 4);
+      for (int r = lane; r < P.n_used; r += 32) {
+        const float v = mine[r];
+        if (v != 0.f) atomicAdd(&P.dtable[(size_t)(r0 + r) * P.win.heads + h], v);
+      }
     }
   } else if (warp >= 4) {
     if (masked) bwd_element_warps<true>(P, S, h, tmem);
@@ -971,7 +1092,7 @@ static int bwd_gt_bytes(const WindowIndex& ix, int maxcode) {
   auto code = [&](int i) { return (i / (ix.wh * ix.ww)) * cH + ((i / ix.ww) % ix.wh) * cW + i % ix.ww; };
   int span = 0;
   for (int f = 0; f < ix.N; f += 32) span = std::max(span, code(std::min(f + 31, ix.N - 1)) - code(f));
-  return (4 * (2 * span + 1) + 15) / 16 * 16;
+  return (4 * (2 * span + 1) + 15) / 16 * 16 + 16;   // + 16: a slice starts at a 16-byte aligned slot offset
 }
 
 bool window_sm100_bwd_eligible(const WindowIndex& ix, int hd, bool want_dtab) {
@@ -1001,3 +1122,9 @@ int window_sm100_bwd(const WindowIndex& ix, const void* qkv, long long ld, const
 }
 
 }  // namespace valor
+
+#if defined(VALOR_EXP) && (VALOR_EXP & 8)
+extern "C" int valor_exp_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, valor::g_trace, sizeof(long long) * (size_t)n);
+}
+#endif
