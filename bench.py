@@ -81,6 +81,8 @@ def parse():
                     help="parity mode: Dropout / DropPath disabled (default: the reference's training regularisation is ON)")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: one whole-arena gradient all-reduce after backward instead of the buckets launched from inside it")
     return ap.parse_args()
 
 
@@ -332,7 +334,7 @@ def main():
     import torch.distributed as dist
     from tools import synth   # seeded synthetic weights / batch (the GPU arm never touches oracle/)
     from valor_b200 import kernels as K
-    from valor_b200.distributed import allreduce_grads
+    from valor_b200.distributed import allreduce_grads, overlap_grad_allreduce
     from valor_b200.optim import get_lr_sched
     from valor_b200.pretrain import VALOR, default_opts
 
@@ -353,6 +355,7 @@ def main():
                         num_train_steps=1000)
     model = VALOR.from_pretrained(opts, synth.make_state_dict(geom, seed=0))
     store = model.attach(dtype=torch.bfloat16, device=dev)
+    reducer = overlap_grad_allreduce(store, enable=world > 1 and not args.no_overlap)
     stochastic = not args.no_dropout
     model.set_stochastic(stochastic, seed=1234 + rank)
     host = synth.make_batch(B, F, A, T, geom, seed=123 + rank)
@@ -586,8 +589,11 @@ def main():
             "config": {"workload": f"VALOR-base (VideoSwin-B + AST + BERT-base fusion) pretrain step, per-GPU batch {B}, "
                                    f"{F} frames 224^2, {A} audio clips, {T} tokens (BASELINE configs[1])",
                        "task": TASK, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "dropout": ("on: hidden Dropout 0.1 (BERT, AST) + DropPath 0->0.2 (VideoSwin), masks regenerated in "
-                                   "the backward; attention-probability dropout not applied") if stochastic else
+                       "allreduce": (None if world == 1 else
+                                     (f"{len(reducer.order)} buckets launched from inside backward (overlapped) + remainder"
+                                      if reducer is not None else "one whole-arena all-reduce after backward")),
+                       "dropout": ("on: hidden Dropout 0.1 (BERT, AST), attention-probability dropout 0.1 (BERT, AST), "
+                                   "DropPath 0->0.2 (VideoSwin); masks regenerated in the backward") if stochastic else
                                   "off (parity mode)",
                        "l2": "inputs larger than L2 (154 MB pixels/step), weights+activations >> 126 MB",
                        "geom": args.geom},

@@ -43,19 +43,23 @@ def _worker(rank, world, port, mode, out):
             w = torch.arange(1, 13, dtype=torch.float32).view(6, 2)
             (y * w).sum().backward()
             out[rank] = (y.detach().clone(), x.grad.clone(), ddp_allgather(torch.tensor([rank, rank + 5])))
-        elif mode == "step":
+        elif mode in ("step", "step_overlap"):
             _install_cpu_backend()
             from tests.test_host_logic import build
             torch.set_num_threads(2)
             cfg = dict(geom="tiny", B=2, F=2, A=1, T=16, weight_seed=0, batch_seed=123 + rank, mask_seed=1234 + rank)
             model, batch = build(cfg)
+            if mode == "step_overlap":   # buckets start from inside backward (marks are placed by the forward pass)
+                from valor_b200.distributed import overlap_grad_allreduce
+                assert overlap_grad_allreduce(model.store) is not None
             losses = model(batch, "pt_contra%tva%tv%ta_caption%tva%tv%ta", True)
             model.store.zero_grad()
             sum(losses.values()).backward()
             local_norm = model.store.grad.norm().item()
             allreduce_grads(model.store)
+            extra = model.store.reducer.last_launched_in_backward if mode == "step_overlap" else -1
             out[rank] = ({k: v.item() for k, v in losses.items()}, local_norm, model.store.grad.norm().item(),
-                         model.store.grad[:1000].clone())
+                         model.store.grad[:1000].clone(), model.store.grad.clone(), extra)
     finally:
         dist.destroy_process_group()
 
@@ -90,10 +94,21 @@ def test_allgather_with_grads_world2():
 @pytest.mark.slow
 def test_two_rank_step_is_consistent():
     out = _run("step")
-    l0, n0, a0, h0 = out[0]
-    l1, n1, a1, h1 = out[1]
+    l0, n0, a0, h0 = out[0][:4]
+    l1, n1, a1, h1 = out[1][:4]
     # every rank evaluates the full global contrastive loss (identical), caption losses are local
     assert abs(l0["contra_loss"] - l1["contra_loss"]) < 1e-6
     assert abs(l0["caption_loss"] - l1["caption_loss"]) > 1e-6
     assert abs(a0 - a1) < 1e-6 * a0            # after the all-reduce both ranks hold the same gradient
     torch.testing.assert_close(h0, h1)
+
+
+def test_overlapped_bucket_allreduce_matches_single_allreduce_world2():
+    """The bucketed all-reduce launched from inside backward (DDP-style overlap) leaves exactly the gradients of the
+    single whole-arena all-reduce, starts most buckets before backward ends, and covers the whole arena."""
+    ref = _run("step")
+    got = _run("step_overlap")
+    for r in (0, 1):
+        assert got[r][5] >= 6, f"only {got[r][5]} ranges were reduced from inside backward"
+        assert torch.equal(got[r][4], ref[r][4]), (got[r][4] - ref[r][4]).abs().max()
+    assert torch.equal(got[0][4], got[1][4])

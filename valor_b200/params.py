@@ -70,6 +70,7 @@ class ParamStore:
         self.sumsq = torch.zeros(1, device=device, dtype=torch.float32)
         self.norm = torch.zeros(2, device=device, dtype=torch.float32)  # [grad_norm, clip_coef]
         self.step = 0
+        self.reducer = None   # distributed.GradReducer when the gradient all-reduce overlaps backward (N > 1)
         # optim/adamw.py:52-53,60-70: a parameter whose .grad is None is skipped (no moment update, no weight
         # decay) and every parameter counts its OWN steps for the bias correction.  Which parameters receive no
         # gradient is a static property of (configuration, task): `set_unused` takes their names (the model's

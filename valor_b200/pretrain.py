@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from . import kernels as K
-from .distributed import ddp_allgather, ddp_allgather_with_grads
+from .distributed import ddp_allgather, ddp_allgather_with_grads, mark
 from .functional import lin_of
 from .modeling import VALORModel, default_opts  # noqa: F401
 from .videoswin import _Linear
@@ -130,6 +130,10 @@ class VALOR(VALORModel):
         used = "".join(caption_task + contra_task)
         video_output = self.forward_video_encoder(video_pixels) if "v" in used else None
         audio_output = self.forward_audio_encoder(audio_spectrograms) if "a" in used else None
+        # everything created from here on (fusion BERT, heads) has finished its backward when these fire: the
+        # gradient all-reduce of those parameters starts there and overlaps the encoders' backward (distributed.py)
+        video_output = mark(video_output, "post") if video_output is not None else None
+        audio_output = mark(audio_output, "post") if audio_output is not None else None
         B, T = txt_tokens.shape
         dt = self.compute_dtype
 

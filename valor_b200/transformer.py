@@ -11,6 +11,7 @@ import torch.nn as nn
 from . import functional as Fn
 from . import kernels as K
 from .functional import LN, lin_of, fused_lin
+from .distributed import mark
 from .videoswin import _Linear, _Norm
 
 
@@ -68,6 +69,7 @@ class TransformerEncoder(nn.Module):
         self.last_layernorm = _Norm(config.hidden_size, eps=1e-12)
 
     def run(self, x, n_seq, seq_len):
+        x = mark(x, "ast")                                      # gradient all-reduce bucket boundary (distributed.py)
         for layer in self.layer:
             x = layer.run(x, n_seq, seq_len)
         return Fn.layer_norm(x, LN(self.last_layernorm.weight, self.last_layernorm.bias, 1e-12))

@@ -16,6 +16,7 @@ import torch.nn as nn
 from . import functional as Fn
 from . import kernels as K
 from .functional import LN, lin_of
+from .distributed import mark, swin_bucket
 
 
 def get_window_size(x_size, window_size, shift_size=None):
@@ -140,8 +141,12 @@ class BasicLayer(nn.Module):
             for i in range(depth)])
         self.downsample = downsample(dim=dim) if downsample is not None else None
 
-    def run(self, x, grid):
-        for blk in self.blocks:
+    def run(self, x, grid, stage=0):
+        bucket = None
+        for i, blk in enumerate(self.blocks):
+            if swin_bucket(stage, self.depth, i) != bucket:    # gradient all-reduce bucket boundary (distributed.py)
+                bucket = swin_bucket(stage, self.depth, i)
+                x = mark(x, bucket)
             x = blk.run(x, grid)
         if self.downsample is not None:
             x, grid = self.downsample.run(x, grid)
@@ -199,8 +204,8 @@ class SwinTransformer3D(nn.Module):
         anchor = self._anchor.requires_grad_(True) if torch.is_grad_enabled() else None
         x = self.patch_embed.run(video.contiguous(), anchor, dtype)
         grid = (B, F, H // 4, W // 4)
-        for layer in self.layers:
-            x, grid = layer.run(x, grid)
+        for i, layer in enumerate(self.layers):
+            x, grid = layer.run(x, grid, stage=i)
         x = Fn.layer_norm(x, LN(self.norm.weight, self.norm.bias, self.norm.eps))
         return x, grid
 
