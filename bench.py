@@ -81,6 +81,7 @@ def parse():
                     help="parity mode: Dropout / DropPath disabled (default: the reference's training regularisation is ON)")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dump-gemms", default=None, help="write the per-shape GEMM time table of the roofline pass (JSON lines)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: one whole-arena gradient all-reduce after backward instead of the buckets launched from inside it")
     return ap.parse_args()
@@ -427,7 +428,17 @@ def main():
             s_.record()
             r = orig(a, b, **kw)
             e_.record()
-            recs.append((2.0 * M * N * Kd, s_, e_, tensor))
+            out_b = 4 if kw.get("accumulate") else (4 if kw.get("out_dtype") == torch.float32 else 2)
+            alg = 2.0 * (M * Kd + N * Kd) + float(out_b) * M * N * (2 if kw.get("accumulate") else 1)
+            for extra in ("residual", "act_aux"):
+                if kw.get(extra) is not None:
+                    alg += 2.0 * M * N
+            if kw.get("want_preact"):
+                alg += 2.0 * M * N
+            recs.append((2.0 * M * N * Kd, s_, e_, tensor, alg, (M, N, Kd, bool(kw.get("a_kmajor", True)), bool(kw.get("b_kmajor", True)),
+                                                                 bool(kw.get("accumulate")), int(kw.get("act", 0) or 0),
+                                                                 kw.get("residual") is not None, kw.get("act_aux") is not None,
+                                                                 bool(kw.get("want_preact")))))
             return r
 
         K.gemm = gemm_probe
@@ -436,10 +447,29 @@ def main():
         finally:
             K.gemm = orig
         torch.cuda.synchronize()
-        t_ms = sum(s_.elapsed_time(e_) for f, s_, e_, t in recs if t)
-        fl = sum(f for f, s_, e_, t in recs if t)
-        n_t = sum(1 for r in recs if r[3])
+        recs = [r for r in recs if r[3]]
+        times = [r[1].elapsed_time(r[2]) for r in recs]
+        t_ms = sum(times)
+        fl = sum(r[0] for r in recs)
+        n_t = len(recs)
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        # per-launch speed of light: the slower of the tensor pipe (measured cuBLAS bf16 peak) and HBM (measured copy
+        # bandwidth) on the launch's algorithmic bytes (operands once + output once, fp32 read-modify-write for the
+        # weight gradients); a third of the step's GEMM time is in the HBM-bound [800k x 128..512] swin stage-1/2 shapes
+        sol = [max(r[0] / (peak_tf * 1e12), r[4] / (peak_hbm * 1e9)) * 1e3 for r in recs]
+        hbm_bound = [r[4] / (peak_hbm * 1e9) > r[0] / (peak_tf * 1e12) for r in recs]
+        if args.dump_gemms and rank == 0:
+            agg = {}
+            for r, t, s_ in zip(recs, times, sol):
+                a_ = agg.setdefault(r[5], [0, 0.0, 0.0])
+                a_[0] += 1; a_[1] += t; a_[2] += s_
+            rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+            with open(args.dump_gemms, "w") as f:
+                for key, (n_, t_, s2) in rows:
+                    f.write(json.dumps({"M": key[0], "N": key[1], "K": key[2], "a_kmajor": key[3], "b_kmajor": key[4],
+                                        "accumulate": key[5], "act": key[6], "residual": key[7], "act_aux": key[8],
+                                        "preact": key[9], "launches": n_, "ms": round(t_, 4), "sol_ms": round(s2, 4),
+                                        "frac_of_sol": round(s2 / t_, 3) if t_ > 0 else None}) + "\n")
         return {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05)", "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": traffic_from_profile(args, B),
@@ -447,7 +477,12 @@ def main():
                                 "launches; from profiles/gemm_traffic.json, null when no capture of this workload is committed)",
                 "peak_kind": f"{peak_kind} (sustained bf16)", "timing": "CUDA events inside a captured graph" if in_graph else
                 "CUDA events, eager launches", "launches_per_step": n_t, "gemm_ms_per_step": t_ms,
-                "gemm_tflop_per_step": fl / 1e12, "gemm_share_of_step": None}
+                "gemm_tflop_per_step": fl / 1e12, "gemm_share_of_step": None,
+                "speed_of_light": {"ms_per_step": sum(sol), "frac": sum(sol) / t_ms if t_ms > 0 else None,
+                                   "hbm_bound_launches": sum(hbm_bound),
+                                   "hbm_bound_ms": sum(t for t, h in zip(times, hbm_bound) if h),
+                                   "hbm_peak_gbs": peak_hbm,
+                                   "note": "per launch max(flops / tensor peak, algorithmic bytes / HBM peak), summed"}}
 
     # ---- capture the whole step (forward, backward, all-reduce, clip, AdamW) in one CUDA graph: the C ABI
     # never syncs or allocates, so ~2000 launches replay without Python / launch latency
