@@ -79,6 +79,51 @@ def test_gemm_tensor_tile_widths(bn, form):
     close(got, ref, dtype, f"gemm tensor bn={bn} {form}")
 
 
+@pytest.mark.parametrize("form", ["nt", "nn", "tn"])
+@pytest.mark.parametrize("shape", [(512, 512, 256), (1000, 520, 328), (4096, 768, 192), (136, 256, 64), (50176, 512, 512)])
+@pytest.mark.parametrize("pair", [1, 2])
+def test_gemm_two_cta_tiles(form, shape, pair):
+    """256 x 256 tiles over a CTA pair (tcgen05.mma.cta_group::2; force_bn 1256) against the single-CTA 128 x 256 tile
+    (force_bn 2256) and the fp32 reference: ragged last tiles in M and N, every operand layout."""
+    k = K()
+    M, N, K_ = shape
+    a_k, b_k = {"nt": (True, True), "nn": (True, False), "tn": (False, False)}[form]
+    dtype = torch.bfloat16
+    a = rnd(M, K_, dtype=dtype, seed=3) if a_k else rnd(K_, M, dtype=dtype, seed=3)
+    b = rnd(N, K_, dtype=dtype, seed=4) if b_k else rnd(K_, N, dtype=dtype, seed=4)
+    ref = R.gemm(a, b, a_kmajor=a_k, b_kmajor=b_k)
+    got = k.gemm(dev(a, dtype), dev(b, dtype), a_kmajor=a_k, b_kmajor=b_k, backend=k.BACKEND_TENSOR, force_bn=pair * 1000 + 256)
+    close(got, ref, dtype, f"gemm two-CTA={pair == 1} {form} {shape}")
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_two_cta_epilogues(act):
+    """Fused epilogues on the two-CTA tiles: bias + GELU with the pre-activation side output, residual add, the
+    activation-gradient multiply, and the split-K fp32 accumulation of the weight gradient."""
+    k = K()
+    dtype = torch.bfloat16
+    M, N, K_ = 1280, 768, 256
+    a, b = rnd(M, K_, dtype=dtype, seed=5), rnd(N, K_, dtype=dtype, seed=6, scale=0.1)
+    bias, res = rnd(N, seed=7), rnd(M, N, dtype=dtype, seed=8)
+    kw = dict(backend=k.BACKEND_TENSOR, force_bn=1256)
+    ref, ref_pre = R.gemm(a, b, bias=bias, act=act, want_preact=True)
+    got, got_pre = k.gemm(dev(a, dtype), dev(b, dtype), bias=dev(bias), act=act, want_preact=True, **kw)
+    close(got, ref, dtype, "two-CTA act out")
+    close(got_pre, ref_pre, dtype, "two-CTA preact")
+    close(k.gemm(dev(a, dtype), dev(b, dtype), bias=dev(bias), residual=dev(res, dtype), **kw),
+          R.gemm(a, b, bias=bias, residual=res), dtype, "two-CTA residual")
+    aux = rnd(M, N, dtype=dtype, seed=9)
+    bt = rnd(K_, N, dtype=dtype, seed=10, scale=0.1)
+    close(k.gemm(dev(a, dtype), dev(bt, dtype), b_kmajor=False, act=act, act_aux=dev(aux, dtype), **kw),
+          R.gemm(a, bt, b_kmajor=False, act=act, act_aux=aux), dtype, "two-CTA act-grad")
+    rows = 20000
+    dy, x = rnd(rows, 768, dtype=dtype, seed=11, scale=0.1), rnd(rows, 512, dtype=dtype, seed=12)
+    base = rnd(768, 512, seed=13)
+    out = dev(base.clone())
+    k.gemm(dev(dy, dtype), dev(x, dtype), a_kmajor=False, b_kmajor=False, out=out, accumulate=True, **kw)
+    close(out, base + dy.t() @ x, dtype, "two-CTA wgrad split-K")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 def test_gemm_epilogues(dtype, act):

@@ -58,6 +58,35 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- two-CTA (cta_group::2) forms: the pair's even CTA ("leader") owns the barriers the MMA thread waits on; a
+// shared::cluster address with bit 24 cleared names the leader's copy of the same shared-memory offset
+// (cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask)
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint64_t* leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -194,10 +223,14 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
 
 // BG: the weight-gradient launch also produces the bias gradient (row sums of A over the contraction) through one extra
 // N = 16 MMA per k-step against a constant all-ones B tile: 8 KB of shared memory, 16 more accumulator columns per stage.
-template <int BLOCK_N, bool BG = false>
+// PAIR: two CTAs of a cluster (an SM pair) share one 256 x BLOCK_N tile: each stages its own 128 rows of A and HALF of
+// the B tile, the leader issues tcgen05.mma.cta_group::2 (UMMA 256 x BLOCK_N x 16) and every CTA ends up with its 128
+// accumulator rows in its own tensor memory.  Per SM and k-block that is 32 KB of operands instead of 48 KB: the
+// 128 x 256 single-CTA tile is bound by the L2 -> shared-memory path, not by the tensor pipe.
+template <int BLOCK_N, bool BG = false, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 4 * 16384;  // per epilogue half: 128x64 bf16 out tile + pre-activation tile
   static constexpr int BIAS_BYTES = 4096;
@@ -210,14 +243,19 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES + ONES_BYTES;
 };
 
-template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR, int MODE, bool BG = false>
+template <int BLOCK_N, bool A_KMAJOR, bool B_KMAJOR, int MODE, bool BG = false, bool PAIR = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                   void* __restrict__ Cptr, long long ldc, int M, int N, int K, int k_splits, int vec_ok,
                   int tma_store, int dbg, GemmEpilogue ep) {
-  using Cfg = GemmCfg<BLOCK_N, BG>;
+  using Cfg = GemmCfg<BLOCK_N, BG, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!PAIR || (!BG && BLOCK_N % 128 == 0), "two-CTA tiles: BLOCK_N / 2 must be a whole number of 64-wide panels");
+  constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;       // rows of one work item
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;        // 0 = leader (issues the MMAs)
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   static_assert(!BG || (MODE == EPI_ACC && !A_KMAJOR && !B_KMAJOR), "bias-gradient fusion belongs to the weight-gradient form");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -236,7 +274,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  const int m_blocks = (M + TILE_M - 1) / TILE_M;
   const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
   const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (kb_total + k_splits - 1) / k_splits;
@@ -253,7 +291,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], PAIR ? 16 : 8);   // PAIR: the epilogue warps of both CTAs release the leader's stage
     }
     for (int i = 0; i < 8; ++i) mbar_init(&bars[2 * STAGES + 6 + i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -263,12 +301,19 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)Cfg::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (PAIR) {   // same warp, same destination offset in both CTAs (cute/arch/tmem_allocator_sm100.hpp Allocator2Sm)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)Cfg::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)Cfg::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -277,18 +322,41 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = unit; w < total_work; w += nunits) {
         const int n_blk = w % n_blocks;
         const int rest = w / n_blocks;
         const int m_blk = rest % m_blocks;
         const int ks = rest / m_blocks;
         const int kb0 = ks * kb_per;
         const int kb1 = min(kb0 + kb_per, kb_total);
+        const int row0 = m_blk * TILE_M + rank * BLOCK_M;                       // this CTA's 128 rows of A
+        const int col0b = n_blk * BLOCK_N + (PAIR ? rank * (BLOCK_N / 2) : 0);   // this CTA's share of the B tile
+        constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          if (PAIR) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (A_KMAJOR) {
+              tma_load_2d_pair(&tmA, &full_bar[stage], sa, kb * BLOCK_K, row0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d_pair(&tmA, &full_bar[stage], sa + j * (BLOCK_K * 128), row0 + j * 64, kb * BLOCK_K);
+            }
+            if (B_KMAJOR) {
+              tma_load_2d_pair(&tmB, &full_bar[stage], sb, kb * BLOCK_K, col0b);
+            } else {
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j)
+                tma_load_2d_pair(&tmB, &full_bar[stage], sb + j * (BLOCK_K * 128), col0b + j * 64, kb * BLOCK_K);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (A_KMAJOR) {
             tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
           } else {
@@ -309,11 +377,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor); PAIR: UMMA_M = 256 over the two CTAs
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
                              ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                             ((uint32_t)(BLOCK_M >> 4) << 24);
+                             ((uint32_t)(TILE_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -321,7 +389,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // bias-gradient MMA: A as above (MN-major), B = sixteen K-major rows of ones
       const uint32_t idesc_bg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
                                 ((uint32_t)(BLOCK_M >> 4) << 24);
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = unit; w < total_work; w += nunits) {
         const int rest = w / n_blocks;
         const int ks = rest / m_blocks;
         const int kb0 = ks * kb_per;
@@ -343,14 +411,20 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                             : make_smem_desc(sa + k * UMMA_K * 128, BLOCK_K * 128, 1024);
             const uint64_t bdesc = B_KMAJOR ? make_smem_desc(sb + k * UMMA_K * 2, 0, 1024)
                                             : make_smem_desc(sb + k * UMMA_K * 128, BLOCK_K * 128, 1024);
-            tcgen05_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) tcgen05_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tcgen05_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (BG && bg_tile)   // bias gradient: the same A tile against sixteen columns of ones
               tcgen05_mma_bf16(tmem_base + 2 * BLOCK_N + acc * 16, adesc,
                                make_smem_desc(smem_u32(ones_s) + k * UMMA_K * 2, 0, 1024), idesc_bg,
                                (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) tcgen05_commit(&tmem_full[acc]);
+          if (PAIR) {                          // both CTAs' producers / epilogues learn about it
+            tcgen05_commit_pair(&empty_bar[stage]);
+            if (kb == kb1 - 1) tcgen05_commit_pair(&tmem_full[acc]);
+          } else {
+            tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (kb == kb1 - 1) tcgen05_commit(&tmem_full[acc]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -377,13 +451,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t chunk_ctr = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = unit; w < total_work; w += nunits) {
       const int n_blk = w % n_blocks;
       const int rest = w / n_blocks;
       const int m_blk = rest % m_blocks;
       const int ks = rest / m_blocks;
       const int n0 = n_blk * BLOCK_N;
-      const int row = m_blk * BLOCK_M + r_tile;
+      const int row_base = m_blk * TILE_M + rank * BLOCK_M;   // first row of this CTA's 128 accumulator rows
+      const int row = row_base + r_tile;
       if (!tma_store) {
         // stage the bias slice (only split 0 adds bias when split-K accumulates)
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -439,7 +514,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) {
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                (uint64_t)&tmC),
-                           "r"(smem_u32(st_out)), "r"(n0 + c * 32), "r"(m_blk * BLOCK_M + q * 32)
+                           "r"(smem_u32(st_out)), "r"(n0 + c * 32), "r"(row_base + q * 32)
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -457,7 +532,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (kInTile && lane == 0 && n0 + half * 64 < N) {   // first chunk's input tile, in flight while the MMAs finish
           mbar_expect_tx(in_bar, 4096);
-          tma_load_2d(&tmP, in_bar, wst + 4096, n0 + half * 64, m_blk * BLOCK_M + q * 32);
+          tma_load_2d(&tmP, in_bar, wst + 4096, n0 + half * 64, row_base + q * 32);
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tcgen05_fence_after();
@@ -495,17 +570,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (kInTile && more && lane == 0) {   // every lane has consumed the input tile: fetch the next one
             mbar_expect_tx(in_bar, 4096);
-            tma_load_2d(&tmP, in_bar, st_pre, n0 + (c + 2) * 64, m_blk * BLOCK_M + q * 32);
+            tma_load_2d(&tmP, in_bar, st_pre, n0 + (c + 2) * 64, row_base + q * 32);
           }
           if (lane == 0 && !(dbg & 2)) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              (uint64_t)&tmC),
-                         "r"(smem_u32(st_out)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M + q * 32)
+                         "r"(smem_u32(st_out)), "r"(n0 + c * 64), "r"(row_base + q * 32)
                          : "memory");
             if (has_pre)
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                (uint64_t)&tmP),
-                           "r"(smem_u32(st_pre)), "r"(n0 + c * 64), "r"(m_blk * BLOCK_M + q * 32)
+                           "r"(smem_u32(st_pre)), "r"(n0 + c * 64), "r"(row_base + q * 32)
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -583,17 +658,19 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA of the pair leaves while the other may still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
   }
 }
 
@@ -646,12 +723,12 @@ static int make_tmap_f32(CUtensorMap* tm, const void* ptr, uint64_t inner, uint6
   return 0;
 }
 
-template <int BN, bool AK, bool BK, int MODE, bool BG = false>
+template <int BN, bool AK, bool BK, int MODE, bool BG = false, bool PAIR = false>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, void* C,
                       long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
                       const GemmEpilogue& ep, int grid, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, BG>;
-  auto kern = gemm_sm100_kernel<BN, AK, BK, MODE, BG>;
+  using Cfg = GemmCfg<BN, BG, PAIR>;
+  auto kern = gemm_sm100_kernel<BN, AK, BK, MODE, BG, PAIR>;
   static bool attr_done = false;
   if (!attr_done) {
     VALOR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -665,14 +742,29 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 #else
   const int dbg = 0;
 #endif
+  if (PAIR) {   // clusters of two CTAs (one SM pair per tile); `grid` counts CTAs and is even
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VALOR_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, dbg, ep));
+    return check_launch("gemm_sm100_kernel (two-CTA)");
+  }
   kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, dbg, ep);
   return check_launch("gemm_sm100_kernel");
 }
 
 template <bool AK, bool BK, int MODE>
-static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+static int launch_bn(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      void* C, long long ldc, int M, int N, int K, int k_splits, int vec_ok, int tma_store,
                      const GemmEpilogue& ep, int grid, cudaStream_t st) {
+  if (pair) return launch_cfg<256, AK, BK, MODE, false, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
   switch (bn) {
     case 64: return launch_cfg<64, AK, BK, MODE>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
     case 128: return launch_cfg<128, AK, BK, MODE>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
@@ -711,6 +803,7 @@ static int pick_block_n(int M, int N, int accumulate, int sms) {
 // tools/gemm_bench.py --wgrad-ab), so those shapes keep two launches unless the caller forces a tile width.
 bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor, int M, int N,
                                 int force_bn) {
+  force_bn %= 1000;   // (the thousands select the one- / two-CTA form)
   if ((force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, num_sms())) > 192) return false;
 #ifdef VALOR_DEBUG
   { const char* e = getenv("VALOR_GEMM_NO_TMA_REDUCE"); if (e && atoi(e)) return false; }
@@ -728,9 +821,22 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   VALOR_REQUIRE(ep.residual == nullptr || ep.res_dtype == VALOR_DT_BF16, "gemm_sm100: residual must be bf16");
   VALOR_REQUIRE(ep.act_aux == nullptr || ep.aux_dtype == VALOR_DT_BF16, "gemm_sm100: act_aux must be bf16");
   const int sms = num_sms();
-  const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  // force_bn + 1000: require the two-CTA form, + 2000: forbid it (tests / A-B measurements)
+  const int pair_req = force_bn / 1000;
+  force_bn %= 1000;
   int bn = force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, sms);
   if (ep.bias_grad != nullptr && bn > 192) bn = 192;
+  // two-CTA tiles (256 x 256 over an SM pair): the 128 x 256 single-CTA tile is bound by operand traffic from L2, the
+  // pair halves the B traffic per SM.  Worth it when the 256-row tiles still fill the machine.
+  bool pair = bn == 256 && ep.bias_grad == nullptr && M > BLOCK_M;
+  if (pair && pair_req != 1) {
+    const long tiles2 = (long)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + bn - 1) / bn);
+    pair = ep.accumulate ? tiles2 >= 4 : tiles2 >= (long)(sms / 2);
+  }
+  if (pair_req == 2) pair = false;
+  VALOR_REQUIRE(pair_req != 1 || pair, "gemm_sm100: the two-CTA form needs BLOCK_N = 256, M > 128 and no fused bias gradient");
+  const int m_blocks = pair ? (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (M + BLOCK_M - 1) / BLOCK_M;
+  const int units = pair ? sms / 2 : sms;                 // persistent work consumers (SM pairs / SMs)
   const int n_blocks = (N + bn - 1) / bn;
   const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
   int k_splits = 1;
@@ -746,7 +852,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     for (int s = 1; s <= max_splits && s <= 512; ++s) {
       const long per = (kb_total + s - 1) / s;
       const long s_eff = (kb_total + per - 1) / per;
-      const long rounds = (tiles * s_eff + sms - 1) / sms;
+      const long rounds = (tiles * s_eff + units - 1) / units;
       const long cost = rounds * (per + epi_cost);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; k_splits = (int)s_eff; }
     }
@@ -762,7 +868,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   CUtensorMap ta, tb;
   if (a_kmajor) { if (make_tmap(&ta, A, K, M, lda, BLOCK_M)) return 1; }
   else          { if (make_tmap(&ta, A, M, K, lda, BLOCK_K)) return 1; }
-  if (b_kmajor) { if (make_tmap(&tb, B, K, N, ldb, bn)) return 1; }
+  if (b_kmajor) { if (make_tmap(&tb, B, K, N, ldb, pair ? bn / 2 : bn)) return 1; }   // pair: each CTA stages half of the B tile
   else          { if (make_tmap(&tb, B, N, K, ldb, BLOCK_K)) return 1; }
 
   int vec_ok = (ldc % 8 == 0) && (((uintptr_t)C & 15) == 0);
@@ -797,7 +903,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     if (ep.preact_out && make_tmap(&tp, ep.preact_out, N, M, ep.ld_pre, 32)) return 1;
   }
   const long total = (long)m_blocks * n_blocks * k_splits;
-  const int grid = (int)(total < sms ? total : sms);
+  const int grid = pair ? 2 * (int)(total < units ? total : units) : (int)(total < sms ? total : sms);
   // epilogue specialisation (TMA-store path only; everything else runs the generic code)
   int mode = EPI_GENERIC;
   if (acc_tma) {
@@ -812,7 +918,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     else if (!res && aux && !pre && ep.act == VALOR_ACT_GELU && ep.bias == nullptr) mode = EPI_GELU_AUX;
   }
 #define VALOR_LAUNCH(AK, BK, MODE) \
-  return launch_bn<AK, BK, MODE>(bn, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st)
+  return launch_bn<AK, BK, MODE>(bn, pair, ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st)
   if (a_kmajor && b_kmajor) {
     switch (mode) {
       case EPI_PLAIN: VALOR_LAUNCH(true, true, EPI_PLAIN);
