@@ -35,6 +35,13 @@ def close(got, ref, dtype, what=""):
     assert err <= tol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (tol {tol})"
 
 
+def close_fro(got, ref, what="", tol=6e-3):
+    """relative Frobenius error (bf16 rounding of the output alone is ~2e-3)"""
+    got, ref = got.float().cpu().double(), ref.float().cpu().double()
+    err = (got - ref).norm().item() / (ref.norm().item() + 1e-12)
+    assert err <= tol, f"{what}: relative Frobenius error {err:.3e} (tol {tol})"
+
+
 def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(*shape, generator=g) * scale
@@ -97,25 +104,30 @@ def test_gemm_two_cta_tiles(form, shape, pair):
 
 
 @pytest.mark.parametrize("act", [0, 1])
-def test_gemm_two_cta_epilogues(act):
-    """Fused epilogues on the two-CTA tiles: bias + GELU with the pre-activation side output, residual add, the
-    activation-gradient multiply, and the split-K fp32 accumulation of the weight gradient."""
+@pytest.mark.parametrize("force", [1256, 2256, 128, 192, 64])
+def test_gemm_specialised_epilogues_every_tile(act, force):
+    """The compile-time epilogue specialisations (bias + GELU with the pre-activation side output, residual add, the
+    activation-gradient multiply on a TMA-staged tile, split-K fp32 accumulation of the weight gradient) on every tile
+    shape: two-CTA 256 x 256 (1256), single-CTA 128 x 256 (2256), 128 x 128 / 192 / 64."""
     k = K()
     dtype = torch.bfloat16
     M, N, K_ = 1280, 768, 256
     a, b = rnd(M, K_, dtype=dtype, seed=5), rnd(N, K_, dtype=dtype, seed=6, scale=0.1)
     bias, res = rnd(N, seed=7), rnd(M, N, dtype=dtype, seed=8)
-    kw = dict(backend=k.BACKEND_TENSOR, force_bn=1256)
+    kw = dict(backend=k.BACKEND_TENSOR, force_bn=force)
     ref, ref_pre = R.gemm(a, b, bias=bias, act=act, want_preact=True)
     got, got_pre = k.gemm(dev(a, dtype), dev(b, dtype), bias=dev(bias), act=act, want_preact=True, **kw)
     close(got, ref, dtype, "two-CTA act out")
+    close_fro(got, ref, "act out")
+    close_fro(got_pre, ref_pre, "preact")
     close(got_pre, ref_pre, dtype, "two-CTA preact")
     close(k.gemm(dev(a, dtype), dev(b, dtype), bias=dev(bias), residual=dev(res, dtype), **kw),
           R.gemm(a, b, bias=bias, residual=res), dtype, "two-CTA residual")
     aux = rnd(M, N, dtype=dtype, seed=9)
     bt = rnd(K_, N, dtype=dtype, seed=10, scale=0.1)
-    close(k.gemm(dev(a, dtype), dev(bt, dtype), b_kmajor=False, act=act, act_aux=dev(aux, dtype), **kw),
-          R.gemm(a, bt, b_kmajor=False, act=act, act_aux=aux), dtype, "two-CTA act-grad")
+    got_g, ref_g = k.gemm(dev(a, dtype), dev(bt, dtype), b_kmajor=False, act=act, act_aux=dev(aux, dtype), **kw), R.gemm(a, bt, b_kmajor=False, act=act, act_aux=aux)
+    close(got_g, ref_g, dtype, "act-grad")
+    close_fro(got_g, ref_g, "act-grad")
     rows = 20000
     dy, x = rnd(rows, 768, dtype=dtype, seed=11, scale=0.1), rnd(rows, 512, dtype=dtype, seed=12)
     base = rnd(768, 512, seed=13)

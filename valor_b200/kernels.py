@@ -50,6 +50,11 @@ def _ld(t):
 # ------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------
+# tile policy applied when a call does not force one: 0 = the library's choice, 1000 = two-CTA tiles wherever they are
+# legal, 2000 = never (measurement / bisecting hook; valor_gemm's force_bn argument)
+GEMM_TILE_POLICY = 0
+
+
 def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residual=None, act_aux=None,
          want_preact=False, out=None, out_dtype=None, accumulate=False, alpha=1.0, backend=BACKEND_AUTO,
          force_bn=0, force_splits=0, bias_grad=None):
@@ -82,7 +87,7 @@ def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residua
     if bias_grad is not None:
         assert bias_grad.dtype == torch.float32 and bias_grad.numel() == M and not a_kmajor and not b_kmajor and accumulate
     _call("valor_gemm", DT(a), P(a), _ld(a), int(a_kmajor), P(b), _ld(b), int(b_kmajor), P(out), _ld(out), M, N, K,
-          ctypes.byref(ep), backend, force_bn, force_splits, ST())
+          ctypes.byref(ep), backend, force_bn or GEMM_TILE_POLICY, force_splits, ST())
     return (out, preact) if want_preact else out
 
 
