@@ -93,7 +93,9 @@ def test_optimizer_trajectory_matches_reference_fp32(name):
 def test_optimizer_trajectory_matches_reference_bf16(name):
     golden = json.load(open(os.path.join(HERE, "golden", f"golden_{name}.json")))
     model, batch = build(golden["config"], dtype=torch.bfloat16, device="cuda")
-    run_trajectory(model, batch, golden, loss_rtol=2e-3, gn_rtol=5e-2, param_rtol=1e-4)   # B=2: bf16 gradient-norm noise reaches 3-4%
+    # B = 2: the contrastive mean has four terms divided by temp = 0.07 (single-step bf16 tolerance 3e-3, see
+    # test_bf16_perf_mode_matches_reference) and bf16 gradient-norm noise reaches 3-4 %
+    run_trajectory(model, batch, golden, loss_rtol=3e-3, gn_rtol=5e-2, param_rtol=1e-4)
 
 
 def test_hot_gemms_run_on_the_tensor_backend(monkeypatch):

@@ -12,8 +12,9 @@ def main(path, skip=0, top=40):
     rd = csv.reader(lines)
     hdr = next(rd)
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    mi = hdr.index("Metric Name")
     for r in rd:
-        if len(r) <= vi:
+        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":   # (the same log may carry DRAM byte counters)
             continue
         v = float(r[vi].replace(",", ""))
         u = r[ui]
