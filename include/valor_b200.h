@@ -63,6 +63,11 @@ typedef struct ValorGemmEpilogue {
   float* bias_grad; /* NULL, or (a_kmajor = b_kmajor = 0, accumulate = 1: the weight-gradient form dW += dy^T x):
                        bias_grad[m] += alpha * sum_k A[k,m], i.e. the bias gradient torch autograd produces for nn.Linear,
                        fused into the same launch (no second pass over dy) */
+  const float* row_scale; /* NULL, or one fp32 factor per group of `rows_per_group` consecutive output rows:
+                             C = residual + row_scale[row / rows_per_group] * (alpha * A.B^T + bias)  (act = none).
+                             DropPath's per-sample keep mask / keep_prob (videoswin.py:40-55,238,243) applied inside the
+                             projection / fc2 GEMM that ends the residual branch */
+  int rows_per_group;
 } ValorGemmEpilogue;
 
 int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor,

@@ -39,7 +39,7 @@ def _act_grad(x, act):
 
 def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residual=None, act_aux=None,
          want_preact=False, out=None, out_dtype=None, accumulate=False, alpha=1.0, backend=0, force_bn=0,
-         force_splits=0, bias_grad=None):
+         force_splits=0, bias_grad=None, row_scale=None, rows_per_group=1):
     A = a.float() if a_kmajor else a.float().t()
     if bias_grad is not None:
         bias_grad += alpha * A.sum(1)
@@ -47,6 +47,8 @@ def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residua
     x = alpha * (A @ Bm.t())
     if bias is not None:
         x = x + bias
+    if row_scale is not None:
+        x = x * row_scale.repeat_interleave(rows_per_group)[:x.shape[0], None]
     pre = x
     if act_aux is not None:
         x = x * _act_grad(act_aux.float(), act)

@@ -137,6 +137,29 @@ def test_gemm_specialised_epilogues_every_tile(act, force):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("force", [0, 1256, 2256, 128])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_gemm_row_scale_epilogue(dtype, force, with_res):
+    """DropPath inside the GEMM that ends a residual branch (videoswin.py:40-55,238,243): C = residual +
+    scale[row // rows_per_group] * (A.B^T + bias), ragged last group, every tile shape and the fp32 SIMT path."""
+    k = K()
+    M, N, K_, rpg = 1200, 512, 256, 392
+    a, b = rnd(M, K_, dtype=dtype, seed=31), rnd(N, K_, dtype=dtype, seed=32, scale=0.1)
+    bias, res = rnd(N, seed=33), rnd(M, N, dtype=dtype, seed=34)
+    scale = torch.tensor([1.25, 0.0, 1.25, 1.25])          # keep / keep_prob per sample; sample 1 dropped
+    kw = dict(backend=k.BACKEND_TENSOR, force_bn=force) if (dtype == torch.bfloat16 and force) else {}
+    if dtype == torch.float32 and force:
+        pytest.skip("tile shapes belong to the bf16 tensor path")
+    got = k.gemm(dev(a, dtype), dev(b, dtype), bias=dev(bias), residual=dev(res, dtype) if with_res else None,
+                 row_scale=dev(scale), rows_per_group=rpg, **kw)
+    ref = (a @ b.t() + bias) * scale.repeat_interleave(rpg)[:M, None] + (res if with_res else 0.0)
+    close(got, ref, dtype, "row-scale epilogue")
+    close_fro(got, ref, "row-scale epilogue", tol=6e-3 if dtype == torch.bfloat16 else 1e-5)
+    dropped = got[rpg:2 * rpg].float().cpu()
+    torch.testing.assert_close(dropped, (res[rpg:2 * rpg] if with_res else torch.zeros(rpg, N)).to(dtype).float(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 def test_gemm_epilogues(dtype, act):
     k = K()

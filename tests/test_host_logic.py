@@ -158,7 +158,7 @@ def test_evaluation_dict_matches_reference_logits(cpu_kernels):
 
 
 def test_stochastic_mode_gradients_match_finite_differences(cpu_kernels):
-    """Dropout / DropPath wiring (functional.DropoutAddFn / DropPathAddFn): with the generator state pinned the masks
+    """Dropout / DropPath wiring (functional.DropoutAddFn / the DropPath factor in the GEMM epilogue): with the generator state pinned the masks
     are a fixed function of the call site, so the hand-written backward must agree with central differences."""
     golden = json.load(open(os.path.join(HERE, "golden", "golden_tiny.json")))
     model, batch = build(golden["config"])

@@ -22,7 +22,8 @@ class ValorGemmEpilogue(ctypes.Structure):
                 ("preact_out", ctypes.c_void_p), ("ldr", ctypes.c_longlong), ("ld_aux", ctypes.c_longlong),
                 ("ld_pre", ctypes.c_longlong), ("res_dtype", ctypes.c_int), ("aux_dtype", ctypes.c_int),
                 ("act", ctypes.c_int), ("out_dtype", ctypes.c_int), ("accumulate", ctypes.c_int),
-                ("alpha", ctypes.c_float), ("bias_grad", ctypes.c_void_p)]
+                ("alpha", ctypes.c_float), ("bias_grad", ctypes.c_void_p), ("row_scale", ctypes.c_void_p),
+                ("rows_per_group", ctypes.c_int)]
 
 
 def parse_header(path=HEADER):

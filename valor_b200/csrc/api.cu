@@ -128,6 +128,10 @@ int valor_gemm(int dtype, const void* A, long long lda, int a_kmajor, const void
   ep.ldr = epc->ldr; ep.ld_aux = epc->ld_aux; ep.ld_pre = epc->ld_pre;
   ep.res_dtype = epc->res_dtype; ep.aux_dtype = epc->aux_dtype; ep.act = epc->act; ep.out_dtype = epc->out_dtype;
   ep.accumulate = epc->accumulate; ep.alpha = epc->alpha; ep.bias_grad = epc->bias_grad;
+  ep.row_scale = epc->row_scale; ep.rows_per_group = epc->rows_per_group;
+  VALOR_REQUIRE(ep.row_scale == nullptr || (ep.rows_per_group >= 1 && ep.act == VALOR_ACT_NONE && ep.act_aux == nullptr &&
+                                             ep.preact_out == nullptr && !ep.accumulate),
+                "valor_gemm: row_scale needs rows_per_group >= 1, no activation / side outputs / accumulation");
   VALOR_REQUIRE(ep.bias_grad == nullptr || (!a_kmajor && !b_kmajor && ep.accumulate), "valor_gemm: bias_grad needs the weight-gradient form (a_kmajor = b_kmajor = 0, accumulate = 1)");
   bool tensor_ok = dtype == VALOR_DT_BF16 && gemm_sm100_eligible(A, B, lda, ldb, M, N, K) &&
                    (ep.residual == nullptr || ep.res_dtype == VALOR_DT_BF16) &&

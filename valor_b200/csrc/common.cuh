@@ -195,6 +195,8 @@ struct GemmEpilogue {
   float alpha;           // scales the accumulator before bias
   float* bias_grad;      // wgrad form only ([K,M] x [K,N] operands): bias_grad[m] += alpha * sum_k A[k,m]  (the Linear's bias
                          // gradient = column sums of dy), taken from a ones-column MMA on the A tiles already in shared memory
+  const float* row_scale;  // null, or one factor per `rows_per_group` consecutive rows, applied to (alpha * acc + bias) before the
+  int rows_per_group;      // residual add (DropPath inside the GEMM that ends a residual branch); act must be NONE
 };
 
 }  // namespace valor

@@ -55,6 +55,7 @@ gemm_simt_kernel(const T* __restrict__ A, long long sam, long long sak, const T*
       if (col >= N) continue;
       float y = acc[i][j] * ep.alpha;
       if (ep.bias) y += ep.bias[col];
+      if (ep.row_scale) y *= ep.row_scale[row / ep.rows_per_group];
       if (ep.preact_out) st_any(ep.preact_out, ep.out_dtype, (size_t)row * ep.ld_pre + col, y);
       if (ep.act_aux) y *= act_grad(ld_any(ep.act_aux, ep.aux_dtype, (size_t)row * ep.ld_aux + col), ep.act);
       else y = act_fwd(y, ep.act);

@@ -136,12 +136,16 @@ enum EpiMode { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES = 2, EPI_GELU_PRE = 3, EP
 template <int MODE>
 __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, const GemmEpilogue& ep, int row, int col0, int M,
                                          int N, int lane, int sub, uint8_t* st_out, uint8_t* st_pre,
-                                         const uint8_t* in_tile) {
+                                         const uint8_t* in_tile, float rsc) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float xg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) xg[j] = fmaf(__uint_as_float(v[g * 8 + j]), ep.alpha, wb[g * 8 + j]);
+    if ((MODE == EPI_RES || MODE == EPI_GENERIC) && ep.row_scale != nullptr) {   // DropPath factor of this row (uniform branch)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xg[j] *= rsc;
+    }
     const int col = col0 + g * 8;
     const int chunk = sub * 4 + g;  // 16-byte chunk inside the 128-byte staging row
     const uint32_t soff = (uint32_t)lane * 128u + (uint32_t)((chunk ^ (lane & 7)) << 4);
@@ -459,6 +463,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n0 = n_blk * BLOCK_N;
       const int row_base = m_blk * TILE_M + rank * BLOCK_M;   // first row of this CTA's 128 accumulator rows
       const int row = row_base + r_tile;
+      const float rsc = ep.row_scale != nullptr ? ep.row_scale[min(row, M - 1) / ep.rows_per_group] : 1.0f;
       if (!tma_store) {
         // stage the bias slice (only split 0 adds bias when split-K accumulates)
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -562,9 +567,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             in_phase ^= 1;
           }
           const bool more = (c + 2 < BLOCK_N / 64) && (n0 + (c + 2) * 64 < N);
-          epi_slab<MODE>(va, wbias + cc * 64, ep, row, n0 + c * 64, M, N, lane, 0, st_out, st_pre, st_pre);
+          epi_slab<MODE>(va, wbias + cc * 64, ep, row, n0 + c * 64, M, N, lane, 0, st_out, st_pre, st_pre, rsc);
           if (more) tmem_ld_32x32(trow + (c + 2) * 64, va);       // next chunk's slabs stream in while this one
-          epi_slab<MODE>(vb, wbias + cc * 64 + 32, ep, row, n0 + c * 64 + 32, M, N, lane, 1, st_out, st_pre, st_pre);
+          epi_slab<MODE>(vb, wbias + cc * 64 + 32, ep, row, n0 + c * 64 + 32, M, N, lane, 1, st_out, st_pre, st_pre, rsc);
           if (more) tmem_ld_32x32(trow + (c + 2) * 64 + 32, vb);  // is converted, staged and stored
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -597,7 +602,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (row < M && col0 < N) {
             float x[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha + bias_s[c * 32 + j];
+            for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(v[j]) * ep.alpha + bias_s[c * 32 + j]) * rsc;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int col = col0 + g * 8;
@@ -912,7 +917,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     const bool res = ep.residual != nullptr, aux = ep.act_aux != nullptr, pre = ep.preact_out != nullptr;
     if (res && !aux && !pre && ep.act == VALOR_ACT_NONE) { if (make_tmap(&tp, ep.residual, N, M, ep.ldr, 32)) return 1; }
     if (!res && aux && !pre && ep.act == VALOR_ACT_GELU && ep.bias == nullptr) { if (make_tmap(&tp, ep.act_aux, N, M, ep.ld_aux, 32)) return 1; }
-    if (!res && !aux && !pre && ep.act == VALOR_ACT_NONE) mode = EPI_PLAIN;
+    if (!res && !aux && !pre && ep.act == VALOR_ACT_NONE && ep.row_scale == nullptr) mode = EPI_PLAIN;
     else if (res && !aux && !pre && ep.act == VALOR_ACT_NONE) mode = EPI_RES;
     else if (!res && !aux && pre && ep.act == VALOR_ACT_GELU) mode = EPI_GELU_PRE;
     else if (!res && aux && !pre && ep.act == VALOR_ACT_GELU && ep.bias == nullptr) mode = EPI_GELU_AUX;

@@ -57,7 +57,9 @@ class LinearFn(Function):
     """y = act(x W^T + b) + residual    (nn.Linear + activation + residual add in one GEMM)."""
 
     @staticmethod
-    def forward(ctx, x, lin, act, residual, out_dtype, anchor):
+    def forward(ctx, x, lin, act, residual, out_dtype, anchor, rscale=None):
+        """rscale = (scale [groups] fp32, rows_per_group): y = residual + scale[row // rpg] * (x W^T + b)  — DropPath
+        applied in the epilogue of the GEMM that ends the residual branch (act must be none)."""
         x = x.contiguous()
         N = lin.w.shape[0]
         out = None
@@ -68,9 +70,11 @@ class LinearFn(Function):
         if act != K.ACT_NONE:
             y, h = K.gemm(x, lin.w, bias=lin.b, act=act, residual=residual, want_preact=True, out_dtype=out_dtype)
         else:
-            y, h = K.gemm(x, lin.w, bias=lin.b, residual=residual, out_dtype=out_dtype, out=out), None
+            kw = dict(row_scale=rscale[0], rows_per_group=rscale[1]) if rscale is not None else {}
+            y, h = K.gemm(x, lin.w, bias=lin.b, residual=residual, out_dtype=out_dtype, out=out, **kw), None
+        assert rscale is None or act == K.ACT_NONE
         ctx.save_for_backward(x, h)
-        ctx.lin, ctx.act, ctx.has_res = lin, act, residual is not None
+        ctx.lin, ctx.act, ctx.has_res, ctx.rscale = lin, act, residual is not None, rscale
         return y
 
     @staticmethod
@@ -80,6 +84,8 @@ class LinearFn(Function):
         if not (dy.dim() == 2 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0):
             dy = dy.contiguous()
         dres = dy if ctx.has_res else None
+        if ctx.rscale is not None:   # gradient of the scaled branch
+            dy = K.row_scale(dy.contiguous(), ctx.rscale[0], ctx.rscale[1])
         if dy.dtype != x.dtype:  # fp32 head outputs feeding low-precision operands
             t = torch.empty(dy.shape, device=dy.device, dtype=x.dtype)
             K.cast2d(dy, t)
@@ -89,11 +95,11 @@ class LinearFn(Function):
         dh = K.act_bwd(dy_lp, h, ctx.act) if h is not None else dy_lp
         _wgrad(lin, dh, x)
         dx = K.gemm(dh, lin.w, b_kmajor=False) if ctx.needs_input_grad[0] else None
-        return dx, None, None, dres, None, None
+        return dx, None, None, dres, None, None, None
 
 
-def linear(x, lin, act=K.ACT_NONE, residual=None, out_dtype=None, anchor=None):
-    return LinearFn.apply(x, lin, act, residual, out_dtype, anchor)
+def linear(x, lin, act=K.ACT_NONE, residual=None, out_dtype=None, anchor=None, row_scale=None):
+    return LinearFn.apply(x, lin, act, residual, out_dtype, anchor, row_scale)
 
 
 class MlpFn(Function):
@@ -102,27 +108,31 @@ class MlpFn(Function):
     gradient rides the fc2-dgrad GEMM epilogue."""
 
     @staticmethod
-    def forward(ctx, x, lin1, lin2, act, residual):
+    def forward(ctx, x, lin1, lin2, act, residual, rscale=None):
         x = x.contiguous()
         a, h = K.gemm(x, lin1.w, bias=lin1.b, act=act, want_preact=True)
-        y = K.gemm(a, lin2.w, bias=lin2.b, residual=residual)
+        kw = dict(row_scale=rscale[0], rows_per_group=rscale[1]) if rscale is not None else {}
+        y = K.gemm(a, lin2.w, bias=lin2.b, residual=residual, **kw)
         ctx.save_for_backward(x, h, a)
-        ctx.l1, ctx.l2, ctx.act, ctx.has_res = lin1, lin2, act, residual is not None
+        ctx.l1, ctx.l2, ctx.act, ctx.has_res, ctx.rscale = lin1, lin2, act, residual is not None, rscale
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, h, a = ctx.saved_tensors
         dy = dy.contiguous()
+        dres = dy if ctx.has_res else None
+        if ctx.rscale is not None:   # gradient of the scaled branch (DropPath inside the fc2 epilogue)
+            dy = K.row_scale(dy, ctx.rscale[0], ctx.rscale[1])
         _wgrad(ctx.l2, dy, a)
         dh = K.gemm(dy, ctx.l2.w, b_kmajor=False, act_aux=h, act=ctx.act)
         _wgrad(ctx.l1, dh, x)
         dx = K.gemm(dh, ctx.l1.w, b_kmajor=False) if ctx.needs_input_grad[0] else None
-        return dx, None, None, None, (dy if ctx.has_res else None)
+        return dx, None, None, None, dres, None
 
 
-def mlp(x, lin1, lin2, act, residual=None):
-    return MlpFn.apply(x, lin1, lin2, act, residual)
+def mlp(x, lin1, lin2, act, residual=None, row_scale=None):
+    return MlpFn.apply(x, lin1, lin2, act, residual, row_scale)
 
 
 class LN:
@@ -435,34 +445,19 @@ class DropoutAddFn(Function):
         return K.dropout(dy, None, ctx.p, ctx.rng.state, ctx.site), (dy if ctx.has_res else None), None, None
 
 
-class DropPathAddFn(Function):
-    """out = shortcut + drop_path(branch): per-sample keep mask / keep_prob (videoswin.py:40-55,238,243)."""
-
-    @staticmethod
-    def forward(ctx, x, residual, p, n_groups, rng):
-        site = rng.next_site()
-        scale = K.droppath_scale(n_groups, p, rng.state, site)
-        ctx.save_for_backward(scale)
-        ctx.rpg = x.shape[0] // n_groups
-        return K.row_scale(x.contiguous(), scale, ctx.rpg, residual.contiguous())
-
-    @staticmethod
-    def backward(ctx, dy):
-        (scale,) = ctx.saved_tensors
-        dy = dy.contiguous()
-        return K.row_scale(dy, scale, ctx.rpg), dy, None, None, None
-
-
 def residual_branch(y_fn, residual, rng, p, n_groups=None):
-    """x + regularise(branch): `y_fn(res)` runs the branch's last GEMM with `res` fused into its epilogue.  Without an
-    active generator (eval / parity mode, or p == 0) the residual add stays fused; otherwise the GEMM runs bare and
-    Dropout (n_groups None) or DropPath (n_groups = batch) is applied together with the add."""
+    """x + regularise(branch): `y_fn(res[, row_scale])` runs the branch's last GEMM with `res` fused into its epilogue.
+    Without an active generator (eval / parity mode, or p == 0) only the residual add is fused; DropPath (n_groups =
+    batch) adds its per-sample factor to the same epilogue; Dropout (n_groups None) runs the GEMM bare and applies the
+    element mask together with the add."""
     if rng is None or not rng.active or p <= 0.0:
         return y_fn(residual)
-    y = y_fn(None)
     if n_groups is None:
-        return DropoutAddFn.apply(y, residual, p, rng)
-    return DropPathAddFn.apply(y, residual, p, n_groups, rng)
+        return DropoutAddFn.apply(y_fn(None), residual, p, rng)
+    # DropPath: the per-sample keep / keep_prob factor rides the branch's last GEMM epilogue together with the residual
+    # add (one pass over the activations instead of GEMM + scale-and-add); the backward scales the branch gradient
+    scale = K.droppath_scale(n_groups, p, rng.state, rng.next_site())
+    return y_fn(residual, (scale, residual.shape[0] // n_groups))
 
 
 class CastFn(Function):

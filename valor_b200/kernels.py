@@ -57,8 +57,9 @@ GEMM_TILE_POLICY = 0
 
 def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residual=None, act_aux=None,
          want_preact=False, out=None, out_dtype=None, accumulate=False, alpha=1.0, backend=BACKEND_AUTO,
-         force_bn=0, force_splits=0, bias_grad=None):
-    """C[M,N] (+)= epi(alpha * A . B^T); a: [M,K] (k-major) or [K,M]; b: [N,K] (k-major) or [K,N]."""
+         force_bn=0, force_splits=0, bias_grad=None, row_scale=None, rows_per_group=1):
+    """C[M,N] (+)= epi(alpha * A . B^T); a: [M,K] (k-major) or [K,M]; b: [N,K] (k-major) or [K,N].
+    row_scale [ceil(M / rows_per_group)] fp32: C = residual + row_scale[row // rows_per_group] * (alpha A.B^T + bias)."""
     M, K = (a.shape if a_kmajor else (a.shape[1], a.shape[0]))
     N, Kb = (b.shape if b_kmajor else (b.shape[1], b.shape[0]))
     assert K == Kb, f"gemm: contraction mismatch {K} vs {Kb}"
@@ -86,6 +87,11 @@ def gemm(a, b, *, a_kmajor=True, b_kmajor=True, bias=None, act=ACT_NONE, residua
     ep.bias_grad = bias_grad.data_ptr() if bias_grad is not None else None
     if bias_grad is not None:
         assert bias_grad.dtype == torch.float32 and bias_grad.numel() == M and not a_kmajor and not b_kmajor and accumulate
+    ep.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    ep.rows_per_group = int(rows_per_group)
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.is_contiguous() and row_scale.numel() * rows_per_group >= M
+        assert act == ACT_NONE and act_aux is None and not want_preact and not accumulate
     _call("valor_gemm", DT(a), P(a), _ld(a), int(a_kmajor), P(b), _ld(b), int(b_kmajor), P(out), _ld(out), M, N, K,
           ctypes.byref(ep), backend, force_bn or GEMM_TILE_POLICY, force_splits, ST())
     return (out, preact) if want_preact else out

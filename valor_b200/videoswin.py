@@ -107,11 +107,11 @@ class SwinTransformerBlock3D(nn.Module):
         y, xr = Fn.layer_norm_residual(x, LN(self.norm1.weight, self.norm1.bias, self.norm1.eps))
         qkv = Fn.linear(y, lin_of(a.qkv.weight, a.qkv.bias))
         o = Fn.window_attention(qkv, a.relative_position_bias_table, geom)
-        x = Fn.residual_branch(lambda r: Fn.linear(o, lin_of(a.proj.weight, a.proj.bias), residual=r), xr, rng, dp, B)
+        x = Fn.residual_branch(lambda r, s=None: Fn.linear(o, lin_of(a.proj.weight, a.proj.bias), residual=r, row_scale=s), xr, rng, dp, B)
         y, xr = Fn.layer_norm_residual(x, LN(self.norm2.weight, self.norm2.bias, self.norm2.eps))
         return Fn.residual_branch(
-            lambda r: Fn.mlp(y, lin_of(self.mlp.fc1.weight, self.mlp.fc1.bias), lin_of(self.mlp.fc2.weight, self.mlp.fc2.bias),
-                             K.ACT_GELU, residual=r), xr, rng, dp, B)
+            lambda r, s=None: Fn.mlp(y, lin_of(self.mlp.fc1.weight, self.mlp.fc1.bias), lin_of(self.mlp.fc2.weight, self.mlp.fc2.bias),
+                                     K.ACT_GELU, residual=r, row_scale=s), xr, rng, dp, B)
 
 
 class PatchMerging(nn.Module):
