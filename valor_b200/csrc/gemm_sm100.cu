@@ -226,7 +226,7 @@ __device__ __forceinline__ void epi_slab(const uint32_t* v, const float* wb, con
 }
 
 // BG: the weight-gradient launch also produces the bias gradient (row sums of A over the contraction) through one extra
-// N = 16 MMA per k-step against a constant all-ones B tile: 8 KB of shared memory, 16 more accumulator columns per stage.
+// N = 16 MMA per k-step against a constant all-ones B tile: 2 KB of shared memory, 16 more accumulator columns per stage.
 // PAIR: two CTAs of a cluster (an SM pair) share one 256 x BLOCK_N tile: each stages its own 128 rows of A and HALF of
 // the B tile, the leader issues tcgen05.mma.cta_group::2 (UMMA 256 x BLOCK_N x 16) and every CTA ends up with its 128
 // accumulator rows in its own tensor memory.  Per SM and k-block that is 32 KB of operands instead of 48 KB: the
@@ -241,7 +241,11 @@ struct GemmCfg {
   static constexpr int ONES_BYTES = BG ? 768 + 2048 : 0;   // pad to 1 KB + [16 rows][64 k] of bf16 1.0 (K-major B operand)
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - BIAS_BYTES - STAGING_BYTES - ONES_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int ACC_COLS = 2 * BLOCK_N + (BG ? 32 : 0);
+  // accumulator stages in tensor memory: two (the epilogue of tile i overlaps the main loop of tile i + 1), except the
+  // 256-wide tiles that also carry the bias gradient: 2 x 256 + 32 columns do not exist, and a split-K weight gradient
+  // spends ~40 k-blocks per work item in the main loop against one short reduce-add epilogue, so one stage costs ~4 %
+  static constexpr int ACC_STAGES = (BG && BLOCK_N > 192) ? 1 : 2;
+  static constexpr int ACC_COLS = ACC_STAGES * (BLOCK_N + (BG ? 16 : 0));
   static constexpr int TMEM_COLS = (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256 ? 256 : 512);
   static_assert(ACC_COLS <= 512, "accumulators do not fit tensor memory");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_BYTES + ONES_BYTES;
@@ -255,7 +259,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   int tma_store, int dbg, GemmEpilogue ep) {
   using Cfg = GemmCfg<BLOCK_N, BG, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
-  static_assert(!PAIR || (!BG && BLOCK_N % 128 == 0), "two-CTA tiles: BLOCK_N / 2 must be a whole number of 64-wide panels");
+  static_assert(!PAIR || BLOCK_N % 128 == 0, "two-CTA tiles: BLOCK_N / 2 must be a whole number of 64-wide panels");
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
   constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;       // rows of one work item
   const int rank = PAIR ? (int)cluster_ctarank() : 0;        // 0 = leader (issues the MMAs)
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -392,7 +397,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t acc_phase = 0;
       // bias-gradient MMA: A as above (MN-major), B = sixteen K-major rows of ones
       const uint32_t idesc_bg = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
-                                ((uint32_t)(BLOCK_M >> 4) << 24);
+                                ((uint32_t)(TILE_M >> 4) << 24);
       for (int w = unit; w < total_work; w += nunits) {
         const int rest = w / n_blocks;
         const int ks = rest / m_blocks;
@@ -418,9 +423,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (PAIR) tcgen05_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else tcgen05_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (BG && bg_tile)   // bias gradient: the same A tile against sixteen columns of ones
-              tcgen05_mma_bf16(tmem_base + 2 * BLOCK_N + acc * 16, adesc,
-                               make_smem_desc(smem_u32(ones_s) + k * UMMA_K * 2, 0, 1024), idesc_bg,
-                               (kb > kb0 || k > 0) ? 1u : 0u);
+            {
+              const uint32_t d_bg = tmem_base + ACC_STAGES * BLOCK_N + acc * 16;
+              const uint64_t ones_d = make_smem_desc(smem_u32(ones_s) + k * UMMA_K * 2, 0, 1024);
+              if (PAIR) tcgen05_mma_bf16_pair(d_bg, adesc, ones_d, idesc_bg, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tcgen05_mma_bf16(d_bg, adesc, ones_d, idesc_bg, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           if (PAIR) {                          // both CTAs' producers / epilogues learn about it
             tcgen05_commit_pair(&empty_bar[stage]);
@@ -431,7 +439,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -492,7 +500,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t vb8[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(vb8[0]), "=r"(vb8[1]), "=r"(vb8[2]), "=r"(vb8[3]), "=r"(vb8[4]), "=r"(vb8[5]), "=r"(vb8[6]), "=r"(vb8[7])
-                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BLOCK_N + acc * 16));
+                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_STAGES * BLOCK_N + acc * 16));
             tmem_ld_wait();
             if (row < M) atomicAdd(ep.bias_grad + row, __uint_as_float(vb8[0]) * ep.alpha);
           }
@@ -664,7 +672,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) { if (PAIR) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
     if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
@@ -802,14 +810,11 @@ static int pick_block_n(int M, int N, int accumulate, int sms) {
 }
 
 // Whether gemm_sm100 can produce the bias gradient inside the weight-gradient launch (same conditions as its TMA
-// reduce-add epilogue); otherwise the caller adds a separate column-sum launch.
-// The fused form holds 2 x BLOCK_N + 32 accumulator columns, so it exists for BLOCK_N <= 192 only; where the plain launch
-// would run 256-wide tiles the narrower tile costs more operand traffic than the column-sum launch it saves (measured:
-// tools/gemm_bench.py --wgrad-ab), so those shapes keep two launches unless the caller forces a tile width.
+// reduce-add epilogue); otherwise the caller adds a separate column-sum launch.  256-wide tiles keep ONE accumulator
+// stage next to the sixteen bias-gradient columns (GemmCfg::ACC_STAGES).
 bool gemm_sm100_fuses_bias_grad(const void* C, long long ldc, const GemmEpilogue& ep, int a_kmajor, int b_kmajor, int M, int N,
                                 int force_bn) {
-  force_bn %= 1000;   // (the thousands select the one- / two-CTA form)
-  if ((force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, num_sms())) > 192) return false;
+  (void)M; (void)N; (void)force_bn;
 #ifdef VALOR_DEBUG
   { const char* e = getenv("VALOR_GEMM_NO_TMA_REDUCE"); if (e && atoi(e)) return false; }
 #endif
@@ -830,16 +835,15 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   const int pair_req = force_bn / 1000;
   force_bn %= 1000;
   int bn = force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, sms);
-  if (ep.bias_grad != nullptr && bn > 192) bn = 192;
   // two-CTA tiles (256 x 256 over an SM pair): the 128 x 256 single-CTA tile is bound by operand traffic from L2, the
   // pair halves the B traffic per SM.  Worth it when the 256-row tiles still fill the machine.
-  bool pair = bn == 256 && ep.bias_grad == nullptr && M > BLOCK_M;
+  bool pair = bn == 256 && M > BLOCK_M;
   if (pair && pair_req != 1) {
     const long tiles2 = (long)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + bn - 1) / bn);
     pair = ep.accumulate ? tiles2 >= 4 : tiles2 >= (long)(sms / 2);
   }
   if (pair_req == 2) pair = false;
-  VALOR_REQUIRE(pair_req != 1 || pair, "gemm_sm100: the two-CTA form needs BLOCK_N = 256, M > 128 and no fused bias gradient");
+  VALOR_REQUIRE(pair_req != 1 || pair, "gemm_sm100: the two-CTA form needs BLOCK_N = 256 and M > 128");
   const int m_blocks = pair ? (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (M + BLOCK_M - 1) / BLOCK_M;
   const int units = pair ? sms / 2 : sms;                 // persistent work consumers (SM pairs / SMs)
   const int n_blocks = (N + bn - 1) / bn;
@@ -940,11 +944,13 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
     }
   }
   if (!a_kmajor && b_kmajor) VALOR_LAUNCH(false, true, EPI_GENERIC);
-  if (mode == EPI_ACC && ep.bias_grad != nullptr) {   // weight gradient + bias gradient in one launch (BLOCK_N <= 192: TMEM)
+  if (mode == EPI_ACC && ep.bias_grad != nullptr) {   // weight gradient + bias gradient in one launch
+    if (pair) return launch_cfg<256, false, false, EPI_ACC, true, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
     switch (bn) {
       case 64: return launch_cfg<64, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
       case 128: return launch_cfg<128, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
-      default: return launch_cfg<192, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+      case 192: return launch_cfg<192, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
+      default: return launch_cfg<256, false, false, EPI_ACC, true>(ta, tb, tc, tp, C, ldc, M, N, K, k_splits, vec_ok, tma_store, ep, grid, st);
     }
   }
   if (mode == EPI_ACC) VALOR_LAUNCH(false, false, EPI_ACC);
