@@ -112,3 +112,23 @@ def test_overlapped_bucket_allreduce_matches_single_allreduce_world2():
         assert got[r][5] >= 6, f"only {got[r][5]} ranges were reduced from inside backward"
         assert torch.equal(got[r][4], ref[r][4]), (got[r][4] - ref[r][4]).abs().max()
     assert torch.equal(got[0][4], got[1][4])
+
+
+def test_gradient_buckets_follow_the_model_segments():
+    """Bucket boundaries derived from parameter names: one bucket per Swin stage, the 18-block stage 3 split in three
+    (first / middle / last six blocks + the stage's PatchMerging), AST layers, everything after the encoders; the
+    marks placed by the forward pass use the same names."""
+    from valor_b200.distributed import default_segments, swin_bucket
+    names = [f"video_encoder.layers.{st}.blocks.{b}.attn.qkv.weight" for st, d in enumerate((2, 2, 18, 2)) for b in range(d)]
+    names += [f"video_encoder.layers.{st}.downsample.reduction.weight" for st in range(3)]
+    names += ["video_encoder.patch_embed.proj.weight", "video_encoder.norm.weight", "audio_encoder.layer.3.ff_layer.linear1.weight",
+              "multimodal_encoder.encoder.layer.0.output.dense.weight", "cls.dense.weight", "contra_temp"]
+    segs = dict(default_segments(names))
+    assert list(segs) == ["swin.0", "swin.1", "swin.2a", "swin.2b", "swin.2c", "swin.3", "ast", "post"]
+    assert segs["swin.2a"] == tuple(f"video_encoder.layers.2.blocks.{b}." for b in range(6))
+    assert segs["swin.2c"][-1] == "video_encoder.layers.2.downsample." and "video_encoder.layers.2.blocks.17." in segs["swin.2c"]
+    assert segs["swin.0"][-1] == "video_encoder.layers.0.downsample."
+    assert [swin_bucket(2, 18, b) for b in (0, 5, 6, 11, 12, 17)] == ["swin.2a", "swin.2a", "swin.2b", "swin.2b", "swin.2c", "swin.2c"]
+    assert swin_bucket(1, 2, 1) == "swin.1"
+    owned = [n for n in names if any(n.startswith(p) for ps in segs.values() for p in ps)]
+    assert set(names) - set(owned) == {"video_encoder.patch_embed.proj.weight", "video_encoder.norm.weight", "contra_temp"}
