@@ -48,6 +48,9 @@ int valor_num_sms(void);
  *   a_kmajor=1: A stored [M,K] row-major (pitch lda);  0: stored [K,M] row-major (pitch lda)
  *   b_kmajor=1: B stored [N,K] row-major (pitch ldb);  0: stored [K,N] row-major (pitch ldb)
  *   epi(x) = act(x + bias) [* act'(act_aux) instead of act when act_aux != NULL] + residual
+ * force_bn / force_splits = 0: the library picks the tile width (64 / 128 / 192 / 256), the one- or two-CTA form
+ * (256-wide tiles over an SM pair, tcgen05.mma.cta_group::2) and the split-K factor.  Non-zero values pin them for
+ * tests and measurements: force_bn = width, + 1000 to require the two-CTA form, + 2000 to forbid it.
  */
 typedef struct ValorGemmEpilogue {
   const float* bias;    /* [N] or NULL */
