@@ -343,7 +343,7 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* gamma, co
     }                                                                                                           \
     break;
   switch (N) {
-    LN_BWD_CASE(1, 4, true) LN_BWD_CASE(2, 2, true) LN_BWD_CASE(4, 2, false) LN_BWD_CASE(6, 1, true)
+    LN_BWD_CASE(1, 4, true) LN_BWD_CASE(2, 2, true) LN_BWD_CASE(4, 1, true) LN_BWD_CASE(6, 1, true)
     LN_BWD_CASE(8, 1, false) LN_BWD_CASE(16, 1, false)
     default:
       layernorm_bwd_generic_kernel<T><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd,
