@@ -786,6 +786,35 @@ static int launch_bn(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap
   }
 }
 
+// Can this device co-schedule the two CTAs of a pair with the kernel's shared-memory footprint?  Asked once
+// (cudaOccupancyMaxActiveClusters on a representative instantiation); if not, every GEMM takes the single-CTA form.
+static bool pair_supported() {
+  static int ok = -1;
+  if (ok < 0) {
+    using Cfg = GemmCfg<256, false, true>;
+    auto kern = gemm_sm100_kernel<256, true, true, EPI_PLAIN, false, true>;
+    ok = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2);
+      cfg.blockDim = dim3(384);
+      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) ok = 1;
+    }
+    if (!ok) {
+      (void)cudaGetLastError();
+      fprintf(stderr, "valor_b200: two-CTA GEMM tiles unavailable on this device (cluster occupancy 0): single-CTA tiles only\n");
+    }
+  }
+  return ok == 1;
+}
+
 // Eligibility: bf16 operands, 16-byte aligned base pointers and row pitches.
 bool gemm_sm100_eligible(const void* A, const void* B, long long lda, long long ldb, int M, int N, int K) {
   if (((uintptr_t)A | (uintptr_t)B) & 15) return false;
@@ -837,7 +866,7 @@ int gemm_sm100(const void* A, long long lda, int a_kmajor, const void* B, long l
   int bn = force_bn ? force_bn : pick_block_n(M, N, ep.accumulate, sms);
   // two-CTA tiles (256 x 256 over an SM pair): the 128 x 256 single-CTA tile is bound by operand traffic from L2, the
   // pair halves the B traffic per SM.  Worth it when the 256-row tiles still fill the machine.
-  bool pair = bn == 256 && M > BLOCK_M;
+  bool pair = bn == 256 && M > BLOCK_M && pair_supported();
   if (pair && pair_req != 1) {
     const long tiles2 = (long)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + bn - 1) / bn);
     pair = ep.accumulate ? tiles2 >= 4 : tiles2 >= (long)(sms / 2);
